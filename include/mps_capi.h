@@ -1,0 +1,151 @@
+/* mps_capi.h — C ABI of libopenmps_b200.so: the B200-native (sm_100a, FP64) implementation of OpenMps's per-timestep
+ * Moving-Particle-Semi-implicit hot path, Computer::ForwardTime() (reference: src/OpenMps/Computer.hpp:1700-1751).
+ *
+ * The reference has no FFI layer: its boundary is the C++ class template OpenMps::Computer<> (Computer.hpp:434-1790).
+ * include/openmps/Computer.hpp in this repository is the drop-in for that class; every method of it forwards to one of
+ * the entry points below ("replaces" = the reference interface the entry point stands in for).  Plain C types only,
+ * caller-allocated buffers, no exceptions across the boundary, no torch types.
+ *
+ * Conventions
+ *   - All particle arrays crossing this boundary are in the caller's ORIGINAL insertion order (Computer::Particles()
+ *     order, Computer.hpp:1780-1783); vectors are row-major n x dim doubles.  Internally particles live cell-sorted.
+ *   - Every function returns an mps_status; mps_last_error(h) gives the message.  Reference exceptions map to
+ *     MPS_CG_NOT_CONVERGED (Computer::Exception, Computer.hpp:1424-1428) and MPS_CELL_OVERFLOW (Grid::Exception,
+ *     Grid.hpp:314-318).  There is NO CPU fallback: without a CUDA device mps_create fails with MPS_CUDA_ERROR.
+ *   - One host thread per handle (same contract as the reference object); work is queued on one CUDA stream per
+ *     handle and the call returns once results the caller asked for are in the caller's buffers.
+ */
+#ifndef OPENMPS_B200_MPS_CAPI_H
+#define OPENMPS_B200_MPS_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mps_solver* mps_handle;
+
+typedef enum mps_status
+{
+	MPS_OK = 0,
+	MPS_CG_NOT_CONVERGED = 1, /* Computer::Exception("Conjugate Gradient method couldn't solve Pressure Poison Equation") */
+	MPS_CELL_OVERFLOW = 2,    /* Grid::Exception("Too many particle in a block") */
+	MPS_CUDA_ERROR = 3,
+	MPS_NCCL_ERROR = 4,
+	MPS_BAD_ARG = 5
+} mps_status;
+
+/* Particle::Type, Particle.hpp:16-29 */
+enum { MPS_FLUID = 0, MPS_WALL = 1, MPS_DUMMY = 2, MPS_DISABLED = 3 };
+
+/* Arguments of Environment's constructor (Environment.hpp:101-128) + the compile-time variant switches the reference
+ * selects with DIM3 (defines.hpp:11) and CENTRAL_GRAVITY (Computer.hpp:925,981), which are run-time here. */
+typedef struct mps_env
+{
+	int32_t dim;             /* 2 or 3 */
+	int32_t central_gravity; /* 0 / 1 */
+	double max_dt;           /* outputInterval / minStepCountPerOutput (Main.cpp:234) */
+	double courant;
+	double g;
+	double rho;
+	double nu;
+	double r_e_by_l0;
+	double l0;
+	double min_x[3];         /* 2-D: {minX, minZ}; 3-D: {minX, minY, minZ} */
+	double max_x[3];
+} mps_env;
+
+/* Derived constants, exactly as Environment computes them (Environment.hpp:129-216) + grid extents (Grid.hpp:137-150) */
+typedef struct mps_env_info
+{
+	double t, dt, n0, max_dt, max_dx, r_e, neighbor_length, l0, rho, nu;
+	int64_t grid_cells[3];
+	uint64_t cell_capacity;  /* Grid::MaxParticles(), Grid.hpp:270-273 */
+} mps_env_info;
+
+typedef struct mps_stats
+{
+	uint64_t steps;            /* ForwardTime calls since creation */
+	uint64_t cg_iterations;    /* total CG iterations since creation */
+	uint64_t last_cg_iterations;
+	double last_rr0, last_rr;  /* ||r0||^2 and final ||r||^2 of the last solve */
+	uint64_t particles, neighbors, nnz, active_rows; /* sizes of the last step */
+	uint64_t kernel_launches;  /* kernels launched by this library since creation */
+	double stage_ms[16];       /* accumulated CUDA-event time per stage when stage timing is on (see mps_stage_name) */
+	uint64_t stage_calls[16];
+} mps_stats;
+
+/* ---- life cycle --------------------------------------------------------------------------------------------------- */
+/* replaces Computer::Computer(allowableResidual, env, posWall, posWallPre), Computer.hpp:1674-1691, and CreateComputer, :1800-1815 */
+int mps_create(const mps_env* env, double eps, int device, mps_handle* out);
+int mps_destroy(mps_handle h);
+const char* mps_last_error(mps_handle h);      /* h may be NULL: error of the last failed mps_create */
+int mps_get_env_info(mps_handle h, mps_env_info* out); /* replaces Computer::GetEnvironment(), Computer.hpp:1786-1789 */
+
+/* ---- particles in / out ------------------------------------------------------------------------------------------- */
+/* replaces Computer::AddParticles, Computer.hpp:1754-1777 (appends; may be called repeatedly).  Non-fluid particles are
+ * pinned to the position they are added with, like the driver's positionWall (Main.cpp:304-315). */
+int mps_add_particles(mps_handle h, uint64_t n, const double* x, const double* u, const double* p, const double* nd, const int32_t* type);
+uint64_t mps_count(mps_handle h);
+/* replaces Computer::Particles(), Computer.hpp:1780-1783.  Any pointer may be NULL. */
+int mps_download(mps_handle h, double* x, double* u, double* p, double* nd, int32_t* type);
+/* overwrite fields of the existing particles (what the gtest fixtures do through `computer->particles`); NULL = keep */
+int mps_upload(mps_handle h, const double* x, const double* u, const double* p, const double* nd);
+/* replaces the positionWall(i, t, dt) callback (Computer.hpp:1012-1019): target positions of the listed particles for
+ * the coming steps.  The C++ drop-in evaluates the user's callable on the host and forwards the result here. */
+int mps_set_wall_positions(mps_handle h, uint64_t n, const uint64_t* ids, const double* x);
+
+/* ---- time stepping (the hot path) --------------------------------------------------------------------------------- */
+int mps_determine_dt(mps_handle h, double* dt);           /* replaces Computer::DetermineDt, Computer.hpp:759-777 */
+int mps_forward_time(mps_handle h, double dt);            /* replaces Computer::ForwardTime(dt), Computer.hpp:1700-1742 */
+int mps_forward_time_auto(mps_handle h);                  /* replaces Computer::ForwardTime(),   Computer.hpp:1745-1751 */
+/* the driver's inner loop `while (T() < nextOutputT) ForwardTime()` (Main.cpp:370-376) without per-step host round trips */
+int mps_run_until(mps_handle h, double t_next, uint64_t* steps);
+/* `steps` x ForwardTime() timed with CUDA events on the handle's stream (device time, milliseconds) */
+int mps_run_steps(mps_handle h, uint64_t steps, double* device_ms);
+int mps_get_time(mps_handle h, double* t, double* dt);    /* replaces Environment::T()/Dt(), Environment.hpp:230-242 */
+int mps_set_dt(mps_handle h, double dt, int advance);     /* replaces env.Dt() = dt; env.SetNextT() (test fixtures)   */
+
+/* ---- single stages (what the upstream gtests reach through `friend`, Computer.hpp:437-460) ------------------------ */
+int mps_search_neighbor(mps_handle h);     /* Computer::SearchNeighbor,              Computer.hpp:698-756 + Grid.hpp */
+int mps_compute_density(mps_handle h);     /* Computer::ComputeNeighborDensities,    Computer.hpp:780-833  */
+int mps_error_correction(mps_handle h);    /* Computer::ComputeErrorCorrection,      Computer.hpp:877-910  */
+int mps_explicit_forces(mps_handle h);     /* Computer::ComputeExplicitForces,       Computer.hpp:914-1021 */
+int mps_save_x(mps_handle h);              /* Computer::SaveX,                       Computer.hpp:1025-1039 */
+int mps_set_ppe(mps_handle h);             /* Computer::SetPressurePoissonEquation,  Computer.hpp:1145-1356 */
+int mps_solve_ppe(mps_handle h);           /* Computer::SolvePressurePoissonEquation,Computer.hpp:1359-1429 */
+int mps_assign_pressure(mps_handle h);     /* P = max(x, 0),                         Computer.hpp:1076-1097 */
+int mps_implicit_forces(mps_handle h);     /* Computer::ComputeImplicitForces,       Computer.hpp:1043-1102 */
+int mps_pressure_gradient(mps_handle h);   /* Computer::ModifyByPressureGradient,    Computer.hpp:1433-1564 */
+int mps_dynamic_stabilize(mps_handle h);   /* Computer::DynamicStabilize,            Computer.hpp:1568-1656 */
+int mps_dndt(mps_handle h, uint64_t i, double* out); /* Computer::NeighborDensityVariationSpeed(i), Computer.hpp:838-872 */
+
+/* ---- inspection (parity tests; original particle ids) ------------------------------------------------------------- */
+int mps_get_cells(mps_handle h, int64_t* cells /* n x dim */);              /* Grid::Block<AXIS>, Grid.hpp:250-254 */
+/* Computer::NeighborCount / Neighbor, Computer.hpp:594-612: rowptr has n+1 entries; idx may be NULL to size the call */
+int mps_get_neighbors(mps_handle h, uint64_t* rowptr, uint64_t* idx);
+int mps_get_csr_nnz(mps_handle h, uint64_t* nnz);
+/* ppe.A in the reference's layout: all n rows (identity rows for Dummy/Disabled), columns ascending (Computer.hpp:1337-1354) */
+int mps_get_csr(mps_handle h, uint64_t* rowptr, uint32_t* col, double* val);
+/* which: 0 ppe.x, 1 ppe.b, 2 cg.r, 3 cg.p, 4 cg.Ap, 5 ecs, 6 nWithoutSpp (n doubles); 7 du, 8 originalX (n x dim) */
+int mps_get_vec(mps_handle h, int which, double* out);
+/* load an arbitrary CSR system into ppe.{A,b,x} (the CG known-answer tests, test_ComputerConjugateGradient.cpp:93-107) */
+int mps_set_system(mps_handle h, uint64_t n, const uint64_t* rowptr, const uint32_t* col, const double* val, const double* b, const double* x0);
+int mps_get_solution(mps_handle h, uint64_t n, double* x);
+
+/* ---- measurement ---------------------------------------------------------------------------------------------------- */
+int mps_set_stage_timing(mps_handle h, int on);   /* CUDA-event timing per stage (adds a sync per stage; off by default) */
+int mps_get_stats(mps_handle h, mps_stats* out);
+int mps_reset_stats(mps_handle h);
+const char* mps_stage_name(int stage);            /* names of mps_stats.stage_ms slots; NULL past the end */
+/* time `reps` launches of one named kernel on the current state without changing it (roofline measurements):
+ * "density", "cg_iteration" (one SpMV + both vector updates), ...; returns mean device milliseconds per launch */
+int mps_time_kernel(mps_handle h, const char* name, int reps, double* mean_ms, double* algorithmic_bytes);
+int mps_flush_l2(mps_handle h);                   /* writes a buffer larger than L2 (timing hygiene) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,156 @@
+// mps_solver.h — host-side state of one solver handle and the launch functions each translation unit provides.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mps_capi.h"
+#include "mps_device.cuh"
+
+namespace mps {
+
+// stage slots of mps_stats.stage_ms
+enum Stage
+{
+	kStSort = 0, kStSearch, kStDensity, kStEcs, kStExplicit, kStPpeAssemble, kStCg, kStPressure, kStGradient, kStDs,
+	kStDt, kStCount
+};
+
+template<typename T>
+struct DevBuf
+{
+	T* p = nullptr;
+	size_t cap = 0;
+	// grows geometrically; `keep` preserves the first `keep_n` elements
+	cudaError_t ensure(size_t n, cudaStream_t s = nullptr, size_t keep_n = 0)
+	{
+		if (n <= cap) return cudaSuccess;
+		size_t want = n + n / 4 + 16;
+		T* q = nullptr;
+		cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+		if (e != cudaSuccess) { want = n; e = cudaMalloc(&q, want * sizeof(T)); }
+		if (e != cudaSuccess) return e;
+		if (p && keep_n)
+		{
+			e = cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+			if (e != cudaSuccess) return e;
+			e = cudaStreamSynchronize(s);
+			if (e != cudaSuccess) return e;
+		}
+		if (p) cudaFree(p);
+		p = q; cap = want;
+		return cudaSuccess;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct CgBuffers
+{
+	uint64_t n = 0;          // rows of the loaded system
+	DevBuf<uint64_t> rowptr; // n + 1
+	DevBuf<uint32_t> col;
+	DevBuf<double> val;
+	DevBuf<double> b, x, r, p0, p1, ap;
+	DevBuf<double> partials; // 2 x max grid size
+	bool external = false;   // loaded through mps_set_system (not assembled from particles)
+};
+
+} // namespace mps
+
+struct mps_solver
+{
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	mps::EnvConst env{};
+	std::string last_error;
+
+	uint64_t n = 0;          // particles (all types, including Disabled)
+	int cur = 0;             // which of the two state copies is live
+
+	// state (double-buffered for the per-step permutation); void* because Vec<D> depends on dim
+	mps::DevBuf<double> pos[2], vel[2];    // n * vec_stride doubles
+	mps::DevBuf<double> prs[2], nden[2];
+	mps::DevBuf<uint8_t> type[2];
+	mps::DevBuf<uint32_t> orig[2];
+	mps::DevBuf<uint32_t> inv;             // original id -> slot
+	mps::DevBuf<double> wall;              // target position of non-fluid particles, ORIGINAL order, vec_stride doubles
+
+	// scratch per particle
+	mps::DevBuf<double> nws, ecs, du, x0;  // du, x0: vec_stride doubles
+
+	// grid
+	mps::DevBuf<uint32_t> key, skey, rank, perm, perm_orig, perm2;
+	mps::DevBuf<uint32_t> cell_count;      // ncells + 1
+	mps::DevBuf<uint64_t> cell_start;      // ncells + 2
+	mps::DevBuf<uint64_t> scan_tmp;
+
+	// neighbour list
+	mps::DevBuf<uint32_t> nbr_cnt;
+	mps::DevBuf<uint64_t> nbr_ptr;
+	mps::DevBuf<uint32_t> nbr;
+	uint64_t nbr_total = 0;
+	bool searched = false;
+
+	// PPE
+	mps::DevBuf<uint32_t> row_len;
+	mps::CgBuffers cg;
+	uint64_t nnz_total = 0;
+
+	// staging for upload / download (original order)
+	mps::DevBuf<double> stage_d;
+	mps::DevBuf<int32_t> stage_i;
+
+	mps::DevScalars* d_sc = nullptr;       // device
+	mps::DevScalars* h_sc = nullptr;       // pinned host mirror
+
+	// L2 flush buffer
+	mps::DevBuf<char> flush;
+
+	// stats
+	mps_stats stats{};
+	bool stage_timing = false;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	int cg_max_blocks_per_sm = 0;
+
+	int vec_stride() const { return env.dim == 2 ? 2 : 4; }
+};
+
+namespace mps {
+
+// every launch function returns cudaGetLastError() of its launches (no sync) --------------------------------------
+// mps_grid.cu
+cudaError_t launch_sort_and_search(mps_solver* s);      // cell keys -> counting sort -> reorder -> neighbour list
+cudaError_t launch_get_cells(mps_solver* s, long long* d_cells /* n x dim, original order */);
+// mps_gather.cu
+cudaError_t launch_density(mps_solver* s, bool count_rows);
+cudaError_t launch_ecs(mps_solver* s);
+cudaError_t launch_explicit(mps_solver* s);
+cudaError_t launch_save_x(mps_solver* s);
+cudaError_t launch_ppe_fill(mps_solver* s);          // counts row lengths itself (stage-level API)
+cudaError_t launch_ppe_fill_counted(mps_solver* s);  // row lengths already produced by launch_density(s, true)
+cudaError_t launch_assign_pressure(mps_solver* s);
+cudaError_t launch_gradient(mps_solver* s);
+cudaError_t launch_ds(mps_solver* s);
+cudaError_t launch_max_u2(mps_solver* s);               // -> d_sc->max_u2_bits
+cudaError_t launch_set_dt(mps_solver* s, double dt, int advance, bool from_max_u);
+cudaError_t launch_dndt_one(mps_solver* s, uint64_t orig_id, double* d_out);
+cudaError_t launch_scatter_from_orig(mps_solver* s, const double* d_x, const double* d_u, const double* d_p, const double* d_n,
+	const int32_t* d_type, uint64_t first, uint64_t count, bool append);
+cudaError_t launch_gather_to_orig(mps_solver* s, double* d_x, double* d_u, double* d_p, double* d_n, int32_t* d_type);
+cudaError_t launch_set_wall(mps_solver* s, uint64_t count, const uint64_t* d_ids, const double* d_x);
+cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
+// mps_scan.cu
+cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /* n + 1 */, uint64_t n, DevBuf<uint64_t>& tmp, cudaStream_t st,
+	uint64_t* launches);
+// mps_cg.cu
+cudaError_t launch_cg(mps_solver* s);
+cudaError_t cg_time_iteration(mps_solver* s, int reps, double* mean_ms, double* bytes);
+
+inline unsigned int blocks_for(uint64_t n, unsigned int threads) { return static_cast<unsigned int>((n + threads - 1) / threads); }
+
+} // namespace mps

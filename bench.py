@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the MPS hot path (Computer::ForwardTime) on B200, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): particle-steps/s = particles x steps / time.  A "step" is one ForwardTime() (DetermineDt ->
+neighbour grid -> densities -> explicit forces -> PPE assembly -> CG -> pressure gradient -> DS) over the whole particle
+block.  Workload at N = 1: BASELINE.json configs[1], the 2-D Koshizuka & Oka dam break scaled to 1 008 104 particles
+(l0 = 2.08e-4, time-step cap scaled with l0), synthetic, started from rest.
+
+  value     device time: CUDA events on the solver's stream around exactly K steps, state resident in HBM
+  e2e       the same K steps through the public C-ABI calls with HOST buffers: every step uploads the particle state
+            from pinned host memory (mps_upload), steps (mps_forward_time_auto) and downloads it (mps_download)
+  roofline  the dominant kernel (the persistent CG solve): algorithmic bytes = iterations x (12 nnz + 92 active rows)
+             / CUDA-event time of that kernel, both summed over the timed steps, vs MEASURED_PEAKS.json
+  cpu_baseline (N = 1, rank 0): the reference's own CPU code (oracle/_ref, OpenMP, all host cores) on ONE step of the
+            same 1M-particle workload (~10-30 s)
+
+--impl reference times the reference's CPU implementation (oracle/_ref if present, else the CPU restatement) for K steps
+on a bounded sample of the workload (a coarser dam break; the sample is named in cpu_baseline.sample).
+N > 1: one process per GPU (torchrun); round 1 runs N independent replicas of the block (weak scaling, no collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NPROC = os.cpu_count() or 1
+# the CPU arms use every host core (OpenMP inside the reference); must be set before the libraries are loaded
+os.environ.setdefault("OMP_NUM_THREADS", str(NPROC))
+os.environ.setdefault("OMP_PROC_BIND", "close")
+
+import numpy as np  # noqa: E402
+
+from openmps_b200 import scenes  # noqa: E402
+
+WORKLOADS = {
+    # name: (factory, description)
+    "dambreak2d_1m": (lambda: scenes.dambreak2d_fast(2.08e-4), "DamBreak 2D (Koshizuka&Oka 1996) l0=2.08e-4, 1008104 particles, from rest"),
+    "dambreak2d_250k": (lambda: scenes.dambreak2d_fast(4.2e-4), "DamBreak 2D l0=4.2e-4"),
+    "dambreak2d_72k": (lambda: scenes.dambreak2d_fast(8e-4), "DamBreak 2D l0=8e-4, 72667 particles"),
+    "dambreak2d_default": (lambda: scenes.dambreak2d(), "DamBreak 2D default (Benchmark/Sample), 1323 particles"),
+    "static_pressure": (lambda: scenes.static_pressure(), "StaticPressure 2D default, 6040 particles"),
+    "central_gravity_4m": (lambda: scenes.central_gravity(half=1000, l0=5e-5), "CentralGravity 2D 2001^2 = 4004001 particles"),
+    "dambreak3d_123k": (lambda: scenes.dambreak3d(8e-3), "DamBreak 3D l0=8e-3, 123147 particles"),
+    "dambreak3d_1m": (lambda: scenes.dambreak3d(3.6e-3), "DamBreak 3D l0=3.6e-3"),
+    "dambreak3d_10m": (lambda: scenes.dambreak3d(1.36e-3), "DamBreak 3D l0=1.36e-3, ~12.2M particles (~10M fluid)"),
+}
+REFERENCE_SAMPLE = "dambreak2d_72k"   # bounded sample for --impl reference (a 1M step costs ~30 s of CPU)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"   # B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return 0
+    from oracle import bind
+    name = args.workload if args.workload_forced else REFERENCE_SAMPLE
+    sc = WORKLOADS[name][0]()
+    use_ref = bind.available(sc.env.dim, sc.env.central_gravity, fast=True)
+    eng = bind.RefComputer.from_scene(sc, fast=True) if use_ref else bind.PortComputer.from_scene(sc)
+    kind = "reference" if use_ref else "port"
+    cores = NPROC if use_ref else min(NPROC, int(os.environ["OMP_NUM_THREADS"]))
+    eng.forward(args.warmup)
+    t0 = time.perf_counter()
+    eng.forward(args.steps)
+    sec = time.perf_counter() - t0
+    alive = int((eng.state()["type"] != 3).sum())
+    value = alive * args.steps / sec
+    sample = f"{WORKLOADS[name][1]}: N={sc.count}, {args.steps} steps after {args.warmup} warm-up steps from rest"
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "particles": sc.count, "description": WORKLOADS[name][1], "host": "CPU only (OpenMP)"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_one_step(sc, name):
+    """Reference CPU code, all host cores, ONE step of the same workload from rest (bounded: ~10-30 s at 1M particles)."""
+    from oracle import bind
+    use_ref = bind.available(sc.env.dim, sc.env.central_gravity, fast=True)
+    if use_ref:
+        eng = bind.RefComputer.from_scene(sc, fast=True); kind = "reference"; cores = NPROC
+        steps = 1 if sc.count > 300000 else (5 if sc.count > 30000 else 50)
+    else:
+        # the scalar restatement is too slow for a 1M step: bounded sub-sample instead
+        small = WORKLOADS[REFERENCE_SAMPLE][0]() if sc.count > 200000 else sc
+        eng = bind.PortComputer.from_scene(small); kind = "port"; cores = 1; steps = 1
+        sc = small
+    t0 = time.perf_counter()
+    eng.forward(steps)
+    sec = time.perf_counter() - t0
+    alive = int((eng.state()["type"] != 3).sum())
+    return {"value": alive * steps / sec, "unit": "particle-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} ForwardTime() step(s) from rest on N={sc.count} ({name if kind == 'reference' else REFERENCE_SAMPLE}), "
+                      f"{sec:.1f} s wall, OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.workload_forced = args.workload is not None
+    if args.workload is None:
+        args.workload = "dambreak2d_1m"
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local = dist_info()
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    from openmps_b200 import capi
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sc = WORKLOADS[args.workload][0]()
+    n = sc.count
+    D = sc.env.dim
+    gpu = capi.GpuComputer.from_scene(sc, device=local)
+
+    # ---- warm-up (untimed), then exactly K steps timed on the device ----
+    gpu.forward(args.warmup)
+    st0 = gpu.stats_dict()
+    gpu.reset_stats()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    dev_ms = gpu.run_steps(args.steps)
+    barrier()
+    clocks = sampler.stop()
+    st = gpu.stats_dict()
+    alive = int((gpu.state()["type"] != 3).sum())
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * alive * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end through the public C ABI with host buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((n, D), dtype=torch.float64).pin_memory().numpy()
+        hu = torch.empty((n, D), dtype=torch.float64).pin_memory().numpy()
+        hp = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        hn = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        ht = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+        gpu.download_into(hx, hu, hp, hn, ht)
+        h2d = n * (2 * D + 2) * 8
+        d2h = n * (2 * D + 2) * 8 + n * 4
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            gpu.set_state(x=hx, u=hu, p=hp, n=hn)     # host -> device: this step's input state
+            gpu.forward(1)                            # ForwardTime()
+            gpu.download_into(hx, hu, hp, hn, ht)     # device -> host: the step's result (what Particles() returns)
+        barrier()
+        sec = time.perf_counter() - t0
+        te = torch.tensor([sec], dtype=torch.float64, device=f"cuda:{local}")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * alive * args.steps / float(te.item()), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / args.steps,
+               "timing": "wall clock around the synchronous C-ABI calls"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = read_peaks()
+    cg_ms, cg_bytes = st["cg_ms"], st["cg_bytes"]
+    achieved = (cg_bytes / (cg_ms * 1e-3)) / 1e9 if cg_ms > 0 else 0.0
+    iters = st["cg_iterations"]
+    roofline = {
+        "kernel": "k_cg_solve (persistent cooperative CG: SpMV + dots + vector updates, one launch per step)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src}); nominal 8000 GB/s -> frac {achieved / 8000.0:.3f}",
+        "traffic": None,
+        "bytes_model": "iterations x (12 nnz + 92 active_rows) per launch (SURVEY.md 8d)",
+        "launches": args.steps, "cg_iterations": iters, "cg_iterations_per_s": iters / (cg_ms * 1e-3) if cg_ms > 0 else None,
+        "kernel_ms_per_launch": cg_ms / max(args.steps, 1), "kernel_share_of_step": cg_ms / dev_ms if dev_ms > 0 else None,
+        "nnz": st["nnz"], "active_rows": st["active_rows"],
+    }
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cpu = cpu_baseline_one_step(sc, args.workload)
+        except Exception as ex:  # the baseline is reported, never allowed to break the bench line
+            cpu = {"value": None, "unit": "particle-steps/s", "cores": NPROC, "kind": "unavailable", "sample": repr(ex)}
+
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][1], "particles": n, "dim": D,
+                   "particles_alive": alive, "l0": sc.env.l0, "r_e_by_l0": sc.env.r_e_by_l0, "eps": sc.env.eps,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one block per GPU, no collective)",
+                   "l2_policy": "inputs larger than L2: CSR + vectors ~330 MB per step vs 126 MB L2 (no explicit flush)",
+                   "cg_iterations_per_step": iters / max(args.steps, 1)},
+        "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,6 +73,8 @@ typedef struct mps_stats
 	double last_rr0, last_rr;  /* ||r0||^2 and final ||r||^2 of the last solve */
 	uint64_t particles, neighbors, nnz, active_rows; /* sizes of the last step */
 	uint64_t kernel_launches;  /* kernels launched by this library since creation */
+	double cg_ms;              /* CUDA-event time of the CG kernel, summed over the steps since the last reset (always on) */
+	double cg_bytes;           /* algorithmic bytes of those solves: sum of iterations x (12 nnz + 92 active rows), SURVEY 8d */
 	double stage_ms[16];       /* accumulated CUDA-event time per stage when stage timing is on (see mps_stage_name) */
 	uint64_t stage_calls[16];
 } mps_stats;

@@ -35,7 +35,7 @@ class MpsStats(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("cg_iterations", C.c_uint64), ("last_cg_iterations", C.c_uint64),
                 ("last_rr0", C.c_double), ("last_rr", C.c_double),
                 ("particles", C.c_uint64), ("neighbors", C.c_uint64), ("nnz", C.c_uint64), ("active_rows", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
+                ("kernel_launches", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
 
 
 class MpsError(RuntimeError):
@@ -305,7 +305,7 @@ class GpuComputer:
             names.append(nm.decode()); k += 1
         return {"steps": st.steps, "cg_iterations": st.cg_iterations, "last_cg_iterations": st.last_cg_iterations,
                 "last_rr0": st.last_rr0, "last_rr": st.last_rr, "particles": st.particles, "neighbors": st.neighbors,
-                "nnz": st.nnz, "active_rows": st.active_rows, "kernel_launches": st.kernel_launches,
+                "nnz": st.nnz, "active_rows": st.active_rows, "kernel_launches": st.kernel_launches, "cg_ms": st.cg_ms, "cg_bytes": st.cg_bytes,
                 "stage_ms": {nm: st.stage_ms[i] for i, nm in enumerate(names)},
                 "stage_calls": {nm: st.stage_calls[i] for i, nm in enumerate(names)}}
 

@@ -112,7 +112,12 @@ int step_body(mps_solver* s)
 	{ StageTimer t(s, kStExplicit); CU(launch_explicit(s)); }
 	{ StageTimer t(s, kStDensity); CU(launch_density(s, true)); }   // + SaveX + PPE row lengths
 	{ StageTimer t(s, kStPpeAssemble); CU(launch_ppe_fill_counted(s)); }
-	{ StageTimer t(s, kStCg); CU(launch_cg(s)); }
+	{
+		StageTimer t(s, kStCg);
+		CU(cudaEventRecord(s->ev_cg0, s->stream));
+		CU(launch_cg(s));
+		CU(cudaEventRecord(s->ev_cg1, s->stream));
+	}
 	{ StageTimer t(s, kStPressure); CU(launch_assign_pressure(s)); }
 	{ StageTimer t(s, kStGradient); CU(launch_gradient(s)); }
 	{ StageTimer t(s, kStDs); CU(launch_ds(s)); }
@@ -129,6 +134,15 @@ int finish_step(mps_solver* s)
 	s->stats.last_rr0 = s->h_sc->rr0; s->stats.last_rr = s->h_sc->rr;
 	s->stats.particles = s->n; s->stats.neighbors = s->nbr_total; s->stats.nnz = s->h_sc->nnz_total;
 	s->nnz_total = s->h_sc->nnz_total;
+	s->stats.active_rows = s->h_sc->active_rows;
+	if (s->n)
+	{
+		// the stream is idle here (sync_scalars), so both events have completed
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, s->ev_cg0, s->ev_cg1) == cudaSuccess) s->stats.cg_ms += ms;
+		s->stats.cg_bytes += static_cast<double>(s->h_sc->cg_iterations) *
+			(12.0 * static_cast<double>(s->h_sc->nnz_total) + 92.0 * static_cast<double>(s->h_sc->active_rows));
+	}
 	return device_status(s);
 }
 
@@ -160,7 +174,7 @@ int mps_create(const mps_env* env, double eps, int device, mps_handle* out)
 	s->sm_count = prop.multiProcessorCount;
 	if (!prop.cooperativeLaunch) return fail(nullptr, MPS_CUDA_ERROR, "device lacks cooperative launch");
 	if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaStreamCreate");
-	cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+	cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); cudaEventCreate(&s->ev_cg0); cudaEventCreate(&s->ev_cg1);
 
 	// ---- Environment, in the reference's evaluation order (Environment.hpp:129-216) ----
 	EnvConst& c = s->env;
@@ -244,6 +258,8 @@ int mps_destroy(mps_handle s)
 	if (s->h_sc) cudaFreeHost(s->h_sc);
 	if (s->ev0) cudaEventDestroy(s->ev0);
 	if (s->ev1) cudaEventDestroy(s->ev1);
+	if (s->ev_cg0) cudaEventDestroy(s->ev_cg0);
+	if (s->ev_cg1) cudaEventDestroy(s->ev_cg1);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 	return MPS_OK;
@@ -688,13 +704,7 @@ int mps_time_kernel(mps_handle s, const char* name, int reps, double* mean_ms, d
 	if (k == "cg_solve")
 	{
 		int rc = sync_scalars(s); if (rc) return rc;
-		uint64_t active = 0;
-		{
-			std::vector<uint64_t> ptr(s->cg.n + 1);
-			CU(cudaMemcpyAsync(ptr.data(), s->cg.rowptr.p, (s->cg.n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-			CU(cudaStreamSynchronize(s->stream));
-			for (uint64_t i = 0; i < s->cg.n; i++) active += (ptr[i + 1] > ptr[i]) ? 1 : 0;
-		}
+		const uint64_t active = s->h_sc->active_rows;
 		s->stats.active_rows = active;
 		s->stats.last_cg_iterations = s->h_sc->cg_iterations;
 		// B_iter = 12 nnz + 92 rows

@@ -57,6 +57,7 @@ struct DevScalars
 	int cg_converged;
 	int error;                      // sticky mps_status raised on the device (cell overflow, CG failure)
 	unsigned int disabled_now;      // particles disabled by the last search
+	unsigned long long active_rows; // PPE rows of the last assembly that are not Dummy / Disabled
 };
 
 template<int D>

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) k_row_len(uint64_t n, Particles<D> P
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	const double* __restrict__ ecs, const uint64_t* __restrict__ row_ptr, uint32_t* __restrict__ col, double* __restrict__ val,
-	double* __restrict__ b, double* __restrict__ x, EnvConst env, const DevScalars* __restrict__ sc)
+	double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
 {
 	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> 
 		b[i] = 0; x[i] = 0;
 		return;
 	}
+	atomicAdd(&sc->active_rows, 1ull); // same address for the whole warp: aggregated by the compiler into one atomic
 	const double dt = sc->dt;
 	const double n0 = env.n0;
 	// right-hand side, Computer.hpp:1204-1214
@@ -630,6 +631,7 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 	MPS_TRY(cg.b.ensure(n, st)); MPS_TRY(cg.x.ensure(n, st)); MPS_TRY(cg.r.ensure(n, st));
 	MPS_TRY(cg.p0.ensure(n, st)); MPS_TRY(cg.p1.ensure(n, st)); MPS_TRY(cg.ap.ensure(n, st));
 	cg.n = n; cg.external = false;
+	MPS_TRY(cudaMemsetAsync(&s->d_sc->active_rows, 0, sizeof(unsigned long long), st));
 	k_ppe_fill<D><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, cg.rowptr.p, cg.col.p, cg.val.p, cg.b.p, cg.x.p, s->env, s->d_sc);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(cudaMemcpyAsync(&s->d_sc->nnz_total, cg.rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));

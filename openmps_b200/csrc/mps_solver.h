@@ -115,6 +115,7 @@ struct mps_solver
 	mps_stats stats{};
 	bool stage_timing = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev_cg0 = nullptr, ev_cg1 = nullptr; // always-on timing of the CG kernel (resolved at the step's own sync)
 	int cg_max_blocks_per_sm = 0;
 
 	int vec_stride() const { return env.dim == 2 ? 2 : 4; }

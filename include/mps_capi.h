@@ -146,6 +146,13 @@ const char* mps_stage_name(int stage);            /* names of mps_stats.stage_ms
  * "density", "cg_iteration" (one SpMV + both vector updates), ...; returns mean device milliseconds per launch */
 int mps_time_kernel(mps_handle h, const char* name, int reps, double* mean_ms, double* algorithmic_bytes);
 int mps_flush_l2(mps_handle h);                   /* writes a buffer larger than L2 (timing hygiene) */
+/* In-kernel cycle counters of the streaming CG kernel (development aid; off by default).  out[0..7] = mean over CTAs of
+ * {phase-1 cycles, consumer wait-for-data cycles, phase-2 cycles, grid-barrier cycles, producer wait-for-free-stage cycles,
+ *  chunks processed, iteration cycles, 0} of the LAST solve; out[8..15] = the maxima; out[16] = chunks, out[17] = blob bytes,
+ *  out[18] = CTAs. */
+int mps_set_cg_profile(mps_handle h, int on);
+int mps_get_cg_profile(mps_handle h, double* out /* 19 doubles */);
+int mps_get_cg_profile_raw(mps_handle h, uint64_t* out /* 8 per CTA */, uint64_t capacity_ctas, uint64_t* ctas);
 
 #ifdef __cplusplus
 }

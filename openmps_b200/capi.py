@@ -100,6 +100,9 @@ def load_library():
     sig("mps_stage_name", [C.c_int], C.c_char_p)
     sig("mps_time_kernel", [vp, C.c_char_p, C.c_int, pd, pd])
     sig("mps_flush_l2", [vp])
+    sig("mps_set_cg_profile", [vp, C.c_int])
+    sig("mps_get_cg_profile", [vp, pd])
+    sig("mps_get_cg_profile_raw", [vp, vp, u64, C.POINTER(u64)])
     _lib = lib
     return lib
 
@@ -316,6 +319,23 @@ class GpuComputer:
         ms, by = C.c_double(), C.c_double()
         self._check(self.lib.mps_time_kernel(self.h, name.encode(), reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def set_cg_profile(self, on):
+        self._check(self.lib.mps_set_cg_profile(self.h, 1 if on else 0))
+
+    def cg_profile(self):
+        """Cycle counters of the last streaming CG solve (see mps_get_cg_profile)."""
+        out = (C.c_double * 19)()
+        self._check(self.lib.mps_get_cg_profile(self.h, out))
+        names = ["phase1", "wait_data", "phase2", "barriers", "wait_stage", "chunks_per_cta", "iteration_cycles_total", "_"]
+        d = {"mean": dict(zip(names, out[0:8])), "max": dict(zip(names, out[8:16])), "chunks": out[16], "blob_bytes": out[17], "ctas": out[18]}
+        return d
+
+    def cg_profile_raw(self):
+        out = np.zeros((1024, 8), dtype=np.uint64)
+        n = C.c_uint64(0)
+        self._check(self.lib.mps_get_cg_profile_raw(self.h, _ptr(out), 1024, C.byref(n)))
+        return out[: n.value]
 
     def flush_l2(self):
         self._check(self.lib.mps_flush_l2(self.h))

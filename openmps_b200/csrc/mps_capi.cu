@@ -234,6 +234,7 @@ int mps_create(const mps_env* env, double eps, int device, mps_handle* out)
 	std::memset(s->h_sc, 0, sizeof(DevScalars));
 	if ((e = cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaMemset");
 	if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaStreamSynchronize");
+	if ((e = cg_configure(s)) != cudaSuccess) return cuda_fail(nullptr, e, "cg_configure");
 	*out = sp.release();
 	return MPS_OK;
 }
@@ -252,7 +253,9 @@ int mps_destroy(mps_handle s)
 	s->cell_count.release(); s->cell_start.release(); s->scan_tmp.release();
 	s->nbr_cnt.release(); s->nbr_ptr.release(); s->nbr.release(); s->row_len.release();
 	s->cg.rowptr.release(); s->cg.col.release(); s->cg.val.release(); s->cg.b.release(); s->cg.x.release(); s->cg.r.release();
-	s->cg.p0.release(); s->cg.p1.release(); s->cg.ap.release(); s->cg.partials.release();
+	s->cg.p0.release(); s->cg.p1.release(); s->cg.ap.release(); s->cg.partials.release(); s->cg.z0.release(); s->cg.z1.release();
+	s->cg.blk_chunks.release(); s->cg.blk_bytes.release(); s->cg.chunk_of_row.release(); s->cg.chunk_base.release();
+	s->cg.blob_base.release(); s->cg.blk_cost.release(); s->cg.cost_base.release(); s->cg.desc.release(); s->cg.blobs.release(); s->cg.prof.release();
 	s->stage_d.release(); s->stage_i.release(); s->flush.release();
 	if (s->d_sc) cudaFree(s->d_sc);
 	if (s->h_sc) cudaFreeHost(s->h_sc);
@@ -562,7 +565,45 @@ int mps_get_csr(mps_handle s, uint64_t* rowptr, uint32_t* col, double* val)
 	CU(cudaStreamSynchronize(s->stream));
 	const uint64_t nnz = ptr[n];
 	std::vector<uint32_t> c(nnz); std::vector<double> v(nnz);
-	if (nnz)
+	if (s->cg.chunked && !s->cg.external)
+	{
+		// decode the chunk blobs back into slot-space CSR (columns: window-local -> slot through the chunk's ranges)
+		int rc = sync_scalars(s); if (rc) return rc;
+		const uint64_t nchunks = s->h_sc->n_chunks, blob_total = s->h_sc->blob_total;
+		std::vector<ChunkDesc> desc(nchunks);
+		std::vector<unsigned char> blobs(blob_total);
+		if (nchunks) CU(cudaMemcpyAsync(desc.data(), s->cg.desc.p, nchunks * sizeof(ChunkDesc), cudaMemcpyDeviceToHost, s->stream));
+		if (blob_total) CU(cudaMemcpyAsync(blobs.data(), s->cg.blobs.p, blob_total, cudaMemcpyDeviceToHost, s->stream));
+		CU(cudaStreamSynchronize(s->stream));
+		uint64_t covered = 0;
+		for (const ChunkDesc& d : desc)
+		{
+			if (d.row_begin != covered) return fail(s, MPS_CUDA_ERROR, "chunk descriptors do not tile the rows");
+			const uint32_t nnz_pad = round_up8(d.nnz);
+			const unsigned char* blob = blobs.data() + d.blob_off + kBlobHeader;
+			const double* val = reinterpret_cast<const double*>(blob);
+			const uint16_t* lcol = reinterpret_cast<const uint16_t*>(blob + static_cast<uint64_t>(nnz_pad) * 8u);
+			const uint16_t* rowoff = lcol + nnz_pad;
+			for (uint32_t lr = 0; lr < d.rows; lr++)
+			{
+				const uint64_t row = static_cast<uint64_t>(d.row_begin) + lr;
+				if (static_cast<uint64_t>(rowoff[lr + 1] - rowoff[lr]) != ptr[row + 1] - ptr[row]) return fail(s, MPS_CUDA_ERROR, "chunk row offsets disagree with the row lengths");
+				for (uint32_t e = rowoff[lr]; e < rowoff[lr + 1]; e++)
+				{
+					const uint32_t l = lcol[e];
+					uint32_t slot = 0xffffffffu;
+					for (uint32_t q = 0; q < d.nranges; q++)
+						if (l >= d.range_off[q] && l < static_cast<uint32_t>(d.range_off[q]) + d.range_len[q]) { slot = d.range_start[q] + (l - d.range_off[q]); break; }
+					if (slot == 0xffffffffu) return fail(s, MPS_CUDA_ERROR, "window-local column outside the chunk's window");
+					const uint64_t k = ptr[row] + (e - rowoff[lr]);
+					c[k] = slot; v[k] = val[e];
+				}
+			}
+			covered += d.rows;
+		}
+		if (covered != n) return fail(s, MPS_CUDA_ERROR, "chunk descriptors do not cover all rows");
+	}
+	else if (nnz)
 	{
 		CU(cudaMemcpyAsync(c.data(), s->cg.col.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
 		CU(cudaMemcpyAsync(v.data(), s->cg.val.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -601,6 +642,7 @@ int mps_get_vec(mps_handle s, int which, double* out)
 	const int width = (which >= 7) ? s->env.dim : 1;
 	if (n == 0) return MPS_OK;
 	if (which <= 4 && !s->cg.b.p) return fail(s, MPS_BAD_ARG, "no PPE assembled yet");
+	if (which == 2 || which == 3) { int rc = sync_scalars(s); if (rc) return rc; }
 	CU(s->stage_d.ensure(n * width, s->stream));
 	CU(launch_gather_vec_to_orig(s, which, s->stage_d.p));
 	CU(cudaMemcpyAsync(out, s->stage_d.p, n * width * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -654,6 +696,41 @@ int mps_get_stats(mps_handle s, mps_stats* out)
 	return MPS_OK;
 }
 int mps_reset_stats(mps_handle s) { NEED(s); s->stats = mps_stats{}; return MPS_OK; }
+
+int mps_set_cg_profile(mps_handle s, int on) { NEED(s); s->cg_profile = on != 0; return MPS_OK; }
+
+int mps_get_cg_profile(mps_handle s, double* out)
+{
+	STAGE_PROLOGUE; NEED(out);
+	for (int k = 0; k < 19; k++) out[k] = 0;
+	int rc = sync_scalars(s); if (rc) return rc;
+	out[16] = static_cast<double>(s->h_sc->n_chunks); out[17] = static_cast<double>(s->h_sc->blob_total);
+	const unsigned g = s->cg.prof_blocks;
+	out[18] = g;
+	if (!g || !s->cg.prof.p) return MPS_OK;
+	std::vector<unsigned long long> h(8ull * g);
+	CU(cudaMemcpyAsync(h.data(), s->cg.prof.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	for (unsigned b = 0; b < g; b++)
+		for (int k = 0; k < 8; k++)
+		{
+			const double v = static_cast<double>(h[8ull * b + k]);
+			out[k] += v / g;
+			if (v > out[8 + k]) out[8 + k] = v;
+		}
+	return MPS_OK;
+}
+
+int mps_get_cg_profile_raw(mps_handle s, uint64_t* out, uint64_t capacity_ctas, uint64_t* ctas)
+{
+	STAGE_PROLOGUE; NEED(out); NEED(ctas);
+	const unsigned g = s->cg.prof_blocks;
+	*ctas = g;
+	if (!g || !s->cg.prof.p || capacity_ctas < g) return MPS_OK;
+	CU(cudaMemcpyAsync(out, s->cg.prof.p, 8ull * g * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return MPS_OK;
+}
 
 int mps_flush_l2(mps_handle s)
 {

@@ -21,8 +21,11 @@
 // phase 2 read 32 + write 16 = 12k + 88 B (gathers of r_j, pprev_j are served by L1/L2: slots are cell-sorted, so the
 // columns of neighbouring rows overlap).  bench.py reports achieved = K * (12 nnz + 92 rows) / kernel time, the
 // figure SURVEY.md §8d defines.
+#include <cstdlib>
+
 #include <cooperative_groups.h>
 
+#include "mps_async.cuh"
 #include "mps_solver.h"
 
 namespace cg = cooperative_groups;
@@ -191,6 +194,485 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_solve(CgArgs a)
 	}
 }
 
+
+// =====================================================================================================================
+// k_cg_stream — the solve of a particle-assembled system (chunk-blob form, mps_device.cuh / mps_chunk.cu).
+//
+// Same CG, same two phases per iteration, same fixed-order reductions as k_cg_solve above; what changes is how the
+// bytes move.  The generic kernel is latency-bound (ncu, profiles/r01a: top stall long_scoreboard on the dependent chain
+// row pointer -> (column, value) -> gathered p_j).  Here nothing in the inner loop touches global memory:
+//   * each CTA (one per SM) owns a fixed, byte-balanced run of chunks.  A producer warp streams every chunk's blob
+//     (values, 16-bit window-local columns, 16-bit row offsets: ONE contiguous 16-byte aligned segment) and the chunk's
+//     window of the gathered vectors (r and p_prev: <= 3 / 9 contiguous slot ranges) into a ring of shared-memory stages
+//     with 1-D bulk async copies (TMA engine, completion on an mbarrier), several stages ahead of the consumer warps;
+//   * the consumers first turn the staged window into p = r + beta p_prev in place (once per window entry instead of
+//     once per matrix entry), then run one row per thread (2-D) / per 4 lanes (3-D) entirely out of shared memory;
+//   * matrix bytes are 10 B per entry instead of 12 (u16 columns) and the row pointer shrinks from 8 B to 2 B per row;
+//   * when the blobs do not fit L2 they are streamed evict_first so that the vectors (5 x 8 B per row) stay L2-resident;
+//   * chunks without entries (runs of Dummy / Disabled rows) are skipped: their rows are zeroed once per solve;
+//   * the grid barrier is a single release-add / acquire-spin on one counter.
+// HBM floor per iteration ~ 10 nnz + 2 rows (blobs); vector traffic is L2-resident up to ~2.5 M rows.
+struct CgStreamArgs
+{
+	uint64_t n;
+	const ChunkDesc* desc;
+	const unsigned char* blobs;
+	const double* b;
+	double* x;
+	double2* z0;               // {r_i, p_i} interleaved, ping-pong pair: ONE window copy per range brings both gathered vectors
+	double2* z1;
+	double* ap;
+	double* partials;          // [2][gridDim.x]
+	DevScalars* sc;
+	double eps;
+	uint32_t blob_stage_bytes; // bytes reserved per stage for the blob (multiple of 128)
+	uint32_t window_stage;     // doubles reserved per stage and vector for the window
+	uint32_t stages;
+	int l2_stream;             // blobs do not fit L2: stream them evict_first
+	unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (mps_get_cg_profile), nullptr = off
+};
+
+constexpr int kMaxStreamWarps = 17;
+constexpr unsigned kGroups = 2; // consumer groups working on alternate chunks
+constexpr uint32_t kDescBatch = 16; // descriptors per half of the producer's descriptor ring
+
+__device__ __forceinline__ double block_sum_n(double v, double* red /* nwarps + 1 */)
+{
+	const unsigned nwarps = blockDim.x >> 5;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) red[wid] = v;
+	__syncthreads();
+	if (wid == 0)
+	{
+		double w = (lane < nwarps) ? red[lane] : 0.0;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+		if (lane == 0) red[nwarps] = w;
+	}
+	__syncthreads();
+	return red[nwarps];
+}
+
+__device__ __forceinline__ double grid_sum_n(const double* partials, const unsigned nblocks, double* red)
+{
+	double v = 0.0;
+	for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) v += __ldcg(partials + k);
+	return block_sum_n(v, red);
+}
+
+// All CTAs of the (cooperatively launched, hence co-resident) grid; `target` is the running arrival count.
+// Release/acquire on the counter is all the ordering needed: every cross-CTA read after the barrier goes to L2 (bulk / 16-byte
+// async copies, __ldcg of the partial sums), everything else a CTA reads it wrote itself — so no L1 invalidation and no
+// full fence (a __threadfence here costs ~1.5 us per barrier: MEMBAR.SC + CCTL.IVALL).
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long& target, const unsigned nblocks)
+{
+	target += nblocks;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		async::red_release_gpu_add(ctr, 1ull);
+		for (unsigned spin = 0; async::ld_acquire_gpu(ctr) < target; spin++)
+		{
+			if (spin > (1u << 27)) __trap(); // a lost CTA must end as a failed launch, never as a hung GPU
+		}
+	}
+	__syncthreads();
+}
+
+struct StreamSmem
+{
+	unsigned char* base;
+	uint32_t stage_bytes, blob_stage_bytes, window_stage;
+	uint64_t* full;
+	uint64_t* empty;
+	uint64_t* dfull;   // [2] descriptor ring halves
+	ChunkDesc* dring;  // [2][kDescBatch]
+	// one stage = [blob = descriptor copy 128 B + values + columns + row offsets][windows]
+	__device__ __forceinline__ unsigned char* stage(uint32_t s) const { return base + static_cast<size_t>(s) * stage_bytes; }
+	__device__ __forceinline__ const ChunkDesc* desc(uint32_t s) const { return reinterpret_cast<const ChunkDesc*>(stage(s)); }
+	__device__ __forceinline__ unsigned char* blob(uint32_t s) const { return stage(s) + kBlobHeader; }
+	// [window of {r, p_prev} : window_stage x 16 B][dense window of the search direction p (or of x) : window_stage x 8 B]
+	__device__ __forceinline__ double2* zwin(uint32_t s) const { return reinterpret_cast<double2*>(stage(s) + blob_stage_bytes); }
+	__device__ __forceinline__ double* pwin(uint32_t s) const { return reinterpret_cast<double*>(zwin(s) + window_stage); }
+};
+
+// One SpMV phase over this CTA's chunks.  ITER = false: r = b - A x, p_prev = 0 (window of x; result into zcur).
+// ITER = true: p = r + beta p_prev, Ap = A p (window of zprev = {r, p_prev}; p into zcur[].y).
+// Returns this thread's share of r.r / p.Ap.  `it` counts the ring uses so far.
+template<int LPR, bool ITER>
+__device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const StreamSmem& sm, const uint32_t c0, const uint32_t c1, const uint32_t live,
+	uint32_t& it, uint32_t& dseq, const double beta, const double2* __restrict__ zprev, double2* __restrict__ zcur,
+	const uint64_t pol_matrix, const uint64_t pol_vector)
+{
+	const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned cwarps = (blockDim.x >> 5) - 1; // consumer warps; the last warp is the producer
+	const uint32_t S = a.stages;
+	double local = 0.0;
+	if (warp == cwarps)
+	{
+		// ---- producer warp: runs up to S - 1 chunks ahead of the consumers; lanes issue the copies of one chunk in parallel:
+		//      lane 0 descriptor, lane 1 blob, lanes 2.. one window range of one vector each ----
+		if (lane == 0) async::fence_proxy_async(); // other CTAs' stores (made visible by the grid barrier) before our async-proxy reads
+		__syncwarp();
+		// The descriptors of this CTA's chunks are themselves streamed through a small double-buffered shared-memory ring
+		// (kDescBatch per half): under full memory load an ordinary global load takes thousands of cycles, and the producer
+		// must never wait for one.
+		uint32_t k = it;
+		const uint32_t nbatch = (c1 - c0 + kDescBatch - 1) / kDescBatch;
+		auto fetch_batch = [&](const uint32_t bidx, const uint32_t seq)
+		{
+			// lane 0 only
+			const uint32_t first = c0 + bidx * kDescBatch;
+			const uint32_t count = (c1 - first < kDescBatch) ? (c1 - first) : kDescBatch;
+			const uint32_t bytes = count * static_cast<uint32_t>(sizeof(ChunkDesc));
+			async::mbar_arrive_expect_tx(&sm.dfull[seq & 1u], bytes);
+			async::bulk_g2s(sm.dring + (seq & 1u) * kDescBatch, a.desc + first, bytes, &sm.dfull[seq & 1u], pol_vector);
+		};
+		if (lane == 0)
+		{
+			if (nbatch > 0) fetch_batch(0, dseq);
+			if (nbatch > 1) fetch_batch(1, dseq + 1);
+		}
+		for (uint32_t bidx = 0; bidx < nbatch; bidx++)
+		{
+			const uint32_t seq = dseq + bidx;
+			const ChunkDesc* half = sm.dring + (seq & 1u) * kDescBatch;
+			async::mbar_wait(&sm.dfull[seq & 1u], (seq >> 1) & 1u);
+			const uint32_t first = c0 + bidx * kDescBatch;
+			const uint32_t count = (c1 - first < kDescBatch) ? (c1 - first) : kDescBatch;
+			for (uint32_t j = 0; j < count; j++)
+			{
+				const ChunkDesc* d = half + j;
+				if (d->nnz == 0) continue; // warp-uniform
+				const uint32_t s = k % S, use = k / S;
+				k++;
+				// Copies of one chunk: lane 0 the blob (descriptor header included), lanes 1.. one window range each.  The SM's copy
+				// engine charges ~420 cycles per bulk copy whatever its size (tools/tma_bench.cu), hence as few copies as possible:
+				// {r, p_prev} travel interleaved.
+				const void* src = nullptr; void* dst = nullptr; uint32_t bytes = 0;
+				if (lane == 0) { src = a.blobs + d->blob_off; dst = sm.stage(s); bytes = d->blob_bytes; }
+				else if (lane <= kMaxRanges)
+				{
+					const uint32_t q = lane - 1;
+					const uint32_t len = d->range_len[q]; // 0 for unused ranges
+					if (ITER) { bytes = len * 16u; src = zprev + d->range_start[q]; dst = sm.zwin(s) + d->range_off[q]; }
+					else { bytes = len * 8u; src = a.x + d->range_start[q]; dst = sm.pwin(s) + d->range_off[q]; }
+				}
+				if (lane == 0)
+				{
+					const long long tw0 = a.prof ? clock64() : 0;
+					async::mbar_wait(&sm.empty[s], (use & 1u) ^ 1u);
+					if (a.prof) a.prof[blockIdx.x * 8 + 4] += static_cast<unsigned long long>(clock64() - tw0);
+					async::mbar_arrive_expect_tx(&sm.full[s], d->blob_bytes + d->window * (ITER ? 16u : 8u));
+				}
+				__syncwarp();
+				if (bytes) async::bulk_g2s(dst, src, bytes, &sm.full[s], lane == 0 ? pol_matrix : pol_vector);
+			}
+			__syncwarp(); // every lane is done reading this half
+			if (lane == 0 && bidx + 2 < nbatch) fetch_batch(bidx + 2, seq + 2);
+		}
+		dseq += nbatch;
+	}
+	else
+	{
+		// ---- consumers: kGroups groups of warps take alternate chunks, so that one group's fixed per-chunk work (barrier
+		//      waits, window pass, epilogue) overlaps the other's shared-memory traffic.  One row per LPR lanes; everything,
+		//      descriptor included, comes from shared memory ----
+		const unsigned gwarps = cwarps / kGroups;      // warps per group
+		const unsigned group = warp / gwarps;
+		const unsigned ctid = threadIdx.x - group * gwarps * 32, nct = gwarps * 32;
+		const uint32_t lr = ctid / LPR, sl = ctid % LPR;
+		for (uint32_t q = group; q < live; q += kGroups)
+		{
+			const uint32_t k = it + q;
+			const uint32_t s = k % S, use = k / S;
+			const long long tw0 = (a.prof && threadIdx.x == 0) ? clock64() : 0;
+			async::mbar_wait(&sm.full[s], use & 1u);
+			if (a.prof && threadIdx.x == 0) { a.prof[blockIdx.x * 8 + 1] += static_cast<unsigned long long>(clock64() - tw0); a.prof[blockIdx.x * 8 + 5] += 1; }
+			const ChunkDesc* d = sm.desc(s);
+			const uint32_t row_begin = d->row_begin, rows = d->rows, nnz_pad = round_up8(d->nnz), window = d->window;
+			const int32_t self_off = d->self_off;
+			const double* __restrict__ val = reinterpret_cast<const double*>(sm.blob(s));
+			const uint16_t* __restrict__ lcol = reinterpret_cast<const uint16_t*>(sm.blob(s) + static_cast<size_t>(nnz_pad) * 8u);
+			const uint16_t* __restrict__ rowoff = lcol + nnz_pad;
+			double* w0 = sm.pwin(s);
+			const bool valid = lr < rows;
+			const uint32_t kb = valid ? rowoff[lr] : 0u, ke = valid ? rowoff[lr + 1] : 0u;
+			uint32_t e = kb + sl;
+			if (ITER)
+			{
+				// the search direction of the whole window, once per entry: p = r + beta p_prev
+				const double2* zw = sm.zwin(s);
+				for (uint32_t l = ctid; l < window; l += nct) { const double2 z = zw[l]; w0[l] = fma(beta, z.y, z.x); }
+				asm volatile("bar.sync %0, %1;" ::"r"(1u + group), "r"(nct) : "memory"); // this group's warps only
+			}
+			double acc0 = 0.0, acc1 = 0.0;
+			for (; e + 7 * LPR < ke; e += 8 * LPR)
+			{
+				uint32_t l[8]; double av[8], pv[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) { l[u] = lcol[e + u * LPR]; av[u] = val[e + u * LPR]; }
+#pragma unroll
+				for (int u = 0; u < 8; u++) pv[u] = w0[l[u]];
+#pragma unroll
+				for (int u = 0; u < 8; u += 2) { acc0 = fma(av[u], pv[u], acc0); acc1 = fma(av[u + 1], pv[u + 1], acc1); }
+			}
+			if (e + 3 * LPR < ke)
+			{
+				uint32_t l[4]; double av[4], pv[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) { l[u] = lcol[e + u * LPR]; av[u] = val[e + u * LPR]; }
+#pragma unroll
+				for (int u = 0; u < 4; u++) pv[u] = w0[l[u]];
+#pragma unroll
+				for (int u = 0; u < 4; u += 2) { acc0 = fma(av[u], pv[u], acc0); acc1 = fma(av[u + 1], pv[u + 1], acc1); }
+				e += 4 * LPR;
+			}
+			for (; e < ke; e += LPR) acc0 = fma(val[e], w0[lcol[e]], acc0);
+			double acc = acc0 + acc1;
+			if (LPR > 1)
+			{
+#pragma unroll
+				for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+			}
+			if (valid && sl == 0)
+			{
+				const uint64_t row = static_cast<uint64_t>(row_begin) + lr;
+				if (ITER)
+				{
+					const double pi = (ke > kb) ? w0[self_off + static_cast<int32_t>(lr)] : 0.0; // rows without entries have r = p = 0
+					zcur[row].y = pi;
+					a.ap[row] = acc;
+					local = fma(pi, acc, local);
+				}
+				else
+				{
+					const double ri = a.b[row] - acc;
+					zcur[row] = make_double2(ri, 0.0);
+					local = fma(ri, ri, local);
+				}
+			}
+			__syncwarp();
+			if (lane == 0) async::mbar_arrive(&sm.empty[s]); // this warp is done reading stage s
+		}
+	}
+	it += live;
+	return local;
+}
+
+template<int LPR>
+__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const uint32_t S = a.stages;
+	const unsigned nthreads = blockDim.x, cwarps = (blockDim.x >> 5) - 1;
+	StreamSmem sm;
+	sm.base = smem_raw;
+	sm.blob_stage_bytes = a.blob_stage_bytes;
+	sm.window_stage = a.window_stage;
+	sm.stage_bytes = a.blob_stage_bytes + 24u * a.window_stage;
+	sm.dring = reinterpret_cast<ChunkDesc*>(smem_raw + static_cast<size_t>(S) * sm.stage_bytes);
+	sm.full = reinterpret_cast<uint64_t*>(sm.dring + 2 * kDescBatch);
+	sm.empty = sm.full + S;
+	sm.dfull = sm.empty + S;
+	double* red = reinterpret_cast<double*>(sm.dfull + 2);                  // kMaxStreamWarps + 1
+	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(red + kMaxStreamWarps + 1); // row0, row1
+	uint32_t* ctl = reinterpret_cast<uint32_t*>(ctl64 + 2);                  // c0, c1, live chunks
+
+	const uint64_t n = a.n;
+	const unsigned nblocks = gridDim.x;
+	if (threadIdx.x == 0)
+	{
+		for (uint32_t s = 0; s < S; s++) { async::mbar_init(&sm.full[s], 1u); async::mbar_init(&sm.empty[s], cwarps / kGroups); }
+		async::mbar_init(&sm.dfull[0], 1u); async::mbar_init(&sm.dfull[1], 1u);
+		async::mbar_init_fence();
+		// this CTA's run of chunks: split the modelled cost evenly (descriptors hold its exclusive prefix)
+		const uint64_t nchunks = a.sc->n_chunks, total = a.sc->cost_total;
+		uint32_t bound[2];
+		for (int w = 0; w < 2; w++)
+		{
+			const uint64_t b = blockIdx.x + w;
+			if (b >= nblocks) { bound[w] = static_cast<uint32_t>(nchunks); continue; }
+			const uint64_t target = total / nblocks * b + (total % nblocks) * b / nblocks;
+			uint64_t lo = 0, hi = nchunks; // first chunk with cost_off >= target
+			while (lo < hi)
+			{
+				const uint64_t mid = (lo + hi) >> 1;
+				if (a.desc[mid].cost_off < target) lo = mid + 1; else hi = mid;
+			}
+			bound[w] = static_cast<uint32_t>(lo);
+		}
+		ctl[0] = bound[0]; ctl[1] = bound[1]; ctl[2] = 0;
+		ctl64[0] = (bound[0] < nchunks) ? a.desc[bound[0]].row_begin : n;
+		ctl64[1] = (bound[1] < nchunks) ? a.desc[bound[1]].row_begin : n;
+	}
+	__syncthreads();
+	const uint32_t c0 = ctl[0], c1 = ctl[1];
+	const uint64_t row0 = ctl64[0], row1 = ctl64[1];
+	{
+		// chunks with entries (the others are skipped by every phase) ; rows of this CTA start from zero everywhere
+		uint32_t mine = 0;
+		for (uint32_t c = c0 + threadIdx.x; c < c1; c += nthreads) mine += (a.desc[c].nnz != 0) ? 1u : 0u;
+		if (mine) atomicAdd(&ctl[2], mine);
+		for (uint64_t i = row0 + threadIdx.x; i < row1; i += nthreads) { a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0; }
+	}
+	__syncthreads();
+	const uint32_t live = ctl[2];
+	const uint64_t pol_matrix = a.l2_stream ? async::policy_evict_first() : async::policy_evict_normal();
+	const uint64_t pol_vector = a.l2_stream ? async::policy_evict_last() : async::policy_evict_normal();
+	double* part0 = a.partials;
+	double* part1 = a.partials + nblocks;
+	unsigned long long bar_target = 0;
+	uint32_t it = 0, dseq = 0;
+	const bool prof_on = (a.prof != nullptr) && (threadIdx.x == 0);
+
+	// ---- r0 = b - A x ; p_prev = 0 ; rr = r0.r0 (Computer.hpp:1382-1386) ----
+	double local = spmv_phase<LPR, false>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
+	local = block_sum_n(local, red);
+	if (threadIdx.x == 0) part0[blockIdx.x] = local;
+	grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+	double rr = grid_sum_n(part0, nblocks, red);
+	const double rr0 = rr;
+	const double tol = rr * a.eps * a.eps;     // Computer.hpp:1386
+	bool converged = (tol == 0);                // Computer.hpp:1389
+	double beta = 0.0;
+	double2* zprev = a.z0; // {r, p_prev}
+	double2* zcur = a.z1;  // receives {r', p}
+	uint64_t iter = 0;
+
+	while (iter < n && !converged)
+	{
+		// ---- phase 1: p = r + beta p_prev ; Ap = A p ; p.Ap ----
+		const long long t0 = prof_on ? clock64() : 0;
+		local = spmv_phase<LPR, true>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
+		local = block_sum_n(local, red);
+		if (threadIdx.x == 0) part1[blockIdx.x] = local;
+		const long long t1 = prof_on ? clock64() : 0;
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		const long long t2 = prof_on ? clock64() : 0;
+		const double pAp = grid_sum_n(part1, nblocks, red);
+		const double alpha = rr / pAp;
+
+		// ---- phase 2 over this CTA's own rows: x += alpha p ; r -= alpha Ap ; r.r (4 independent rows in flight per thread) ----
+		local = 0.0;
+		for (uint64_t base = row0 + threadIdx.x; base < row1; base += 4ull * nthreads)
+		{
+			double pv[4], xv[4], av[4], rv[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
+				const bool on = i < row1;
+				pv[q] = on ? zcur[i].y : 0.0; xv[q] = on ? a.x[i] : 0.0; av[q] = on ? a.ap[i] : 0.0; rv[q] = on ? zprev[i].x : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
+				if (i < row1)
+				{
+					a.x[i] = fma(alpha, pv[q], xv[q]);
+					const double ri = fma(-alpha, av[q], rv[q]);
+					zcur[i].x = ri;
+					local = fma(ri, ri, local);
+				}
+			}
+		}
+		local = block_sum_n(local, red);
+		if (threadIdx.x == 0) part0[blockIdx.x] = local;
+		const long long t3 = prof_on ? clock64() : 0;
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		const double rr_new = grid_sum_n(part0, nblocks, red);
+		if (prof_on)
+		{
+			const long long t4 = clock64();
+			unsigned long long* pr = a.prof + blockIdx.x * 8;
+			pr[0] += static_cast<unsigned long long>(t1 - t0);  // phase 1 (SpMV + block reduction)
+			pr[2] += static_cast<unsigned long long>(t3 - t2);  // phase 2 (+ grid sum of p.Ap)
+			pr[3] += static_cast<unsigned long long>((t2 - t1) + (t4 - t3)); // both grid barriers (+ grid sum of r.r)
+			pr[6] += static_cast<unsigned long long>(t4 - t0);
+		}
+		iter++;
+		converged = (rr_new < tol);            // Computer.hpp:1407-1408
+		if (!converged)
+		{
+			beta = rr_new / rr;                 // Computer.hpp:1417
+		}
+		{ double2* t = zprev; zprev = zcur; zcur = t; } // zprev now holds {r, p} of this iteration
+		rr = rr_new;
+	}
+
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		a.sc->z_final = (zprev == a.z1) ? 1 : 0;
+		a.sc->cg_iterations = iter;
+		a.sc->rr0 = rr0;
+		a.sc->rr = rr;
+		a.sc->cg_converged = converged ? 1 : 0;
+		if (!converged) atomicMax(&a.sc->error, static_cast<int>(MPS_CG_NOT_CONVERGED)); // Computer.hpp:1424-1428
+	}
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+struct StreamGeometry
+{
+	uint32_t blob_stage_bytes, window_stage, stage_bytes;
+	size_t fixed_bytes;
+};
+
+StreamGeometry stream_geometry(const ChunkLimits& lim)
+{
+	StreamGeometry g;
+	g.blob_stage_bytes = round_up(chunk_blob_bytes(lim.max_rows, lim.max_nnz), 128);
+	g.window_stage = round_up(lim.max_window, 16);
+	g.stage_bytes = g.blob_stage_bytes + 24u * g.window_stage;
+	g.fixed_bytes = 2u * kDescBatch * sizeof(ChunkDesc) + 2u * 8u * 8u /* barriers, <= 8 stages */ + 16u + (kMaxStreamWarps + 1) * 8u + 16u + 16u;
+	return g;
+}
+
+template<int LPR>
+cudaError_t launch_stream(mps_solver* s)
+{
+	CgBuffers& c = s->cg;
+	const StreamGeometry g = stream_geometry(c.limits);
+	const size_t smem_bytes = static_cast<size_t>(c.stages) * g.stage_bytes + g.fixed_bytes;
+	const int threads = (c.consumer_warps + 1) * 32;
+	cudaError_t e = cudaFuncSetAttribute(k_cg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_stream<LPR>, threads, smem_bytes);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	const unsigned grid = static_cast<unsigned>(s->sm_count); // one CTA per SM: the ring wants the whole shared memory
+	e = c.partials.ensure(2ull * grid, s->stream);
+	if (e != cudaSuccess) return e;
+	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
+	if (e != cudaSuccess) return e;
+	CgStreamArgs a;
+	a.n = c.n; a.desc = c.desc.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
+	a.ap = c.ap.p; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
+	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
+	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
+	a.l2_stream = ((s->nbr_total + c.n) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
+	a.prof = nullptr;
+	if (s->cg_profile)
+	{
+		e = c.prof.ensure(8ull * grid, s->stream);
+		if (e != cudaSuccess) return e;
+		e = cudaMemsetAsync(c.prof.p, 0, 8ull * grid * sizeof(unsigned long long), s->stream);
+		if (e != cudaSuccess) return e;
+		a.prof = c.prof.p;
+		c.prof_blocks = grid;
+	}
+	void* params[] = { &a };
+	s->stats.kernel_launches += 1;
+	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR>), dim3(grid), dim3(threads), params, smem_bytes, s->stream);
+}
+
 template<int LPR>
 cudaError_t launch_lpr(mps_solver* s, CgArgs& args, unsigned want_blocks)
 {
@@ -219,6 +701,16 @@ cudaError_t launch_cg(mps_solver* s)
 		// an empty system is converged by definition (residual0 == 0)
 		return cudaSuccess;
 	}
+	if (c.chunked && !c.external)
+	{
+		switch (c.lanes_per_row)
+		{
+		case 1: return launch_stream<1>(s);
+		case 2: return launch_stream<2>(s);
+		case 4: return launch_stream<4>(s);
+		default: return launch_stream<8>(s);
+		}
+	}
 	CgArgs args;
 	args.n = c.n; args.rowptr = c.rowptr.p; args.col = c.col.p; args.val = c.val.p; args.b = c.b.p;
 	args.x = c.x.p; args.r = c.r.p; args.pbuf0 = c.p0.p; args.pbuf1 = c.p1.p; args.ap = c.ap.p;
@@ -227,6 +719,56 @@ cudaError_t launch_cg(mps_solver* s)
 	const int lpr = (s->env.dim == 3 && !c.external) ? 16 : 8;
 	const unsigned want = blocks_for(c.n * static_cast<uint64_t>(lpr), kCgThreads);
 	return lpr == 16 ? launch_lpr<16>(s, args, want) : launch_lpr<8>(s, args, want);
+}
+
+// Chunk limits for this environment.  Rows per chunk = consumer threads / lanes per row (every consumer sub-warp owns one row
+// of the chunk); entries and window are sized for interior rows (~21 entries in 2-D at r_e = 2.4 l0, ~57 in 3-D) with some
+// head-room, and a single row must always fit (<= 3^D cells x capacity neighbours); the ring takes as many stages as fit
+// the SM's shared memory.  MPS_CG_WARPS / MPS_CG_STAGES override the defaults (tuning).
+cudaError_t cg_configure(mps_solver* s)
+{
+	CgBuffers& c = s->cg;
+	const int D = s->env.dim;
+	const uint32_t stencil = (D == 3) ? 27u : 9u;
+	const uint32_t row_max = stencil * s->env.cell_cap;
+	int warps = (D == 3) ? 16 : 8; // measured on B200 (scripts/gpu_tune.sh): 2-D 128-row chunks x 4 stages, 3-D 64-row chunks
+	if (const char* v = std::getenv("MPS_CG_WARPS")) warps = std::atoi(v);
+	warps = warps / static_cast<int>(kGroups) * static_cast<int>(kGroups);
+	if (warps < static_cast<int>(kGroups)) warps = kGroups;
+	if (warps > kMaxStreamWarps - 1) warps = kMaxStreamWarps - 1;
+	c.consumer_warps = warps;
+	c.lanes_per_row = (D == 3) ? 4 : 1;
+	if (const char* v = std::getenv("MPS_CG_LPR")) { const int w = std::atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) c.lanes_per_row = w; }
+	ChunkLimits lim;
+	lim.max_rows = static_cast<uint32_t>(warps) / kGroups * 32u / static_cast<uint32_t>(c.lanes_per_row);
+	if (lim.max_rows > 256) lim.max_rows = 256;
+	// mean neighbours within r_e on the lattice: 2-D pi (r_e/l0)^2, 3-D 4/3 pi (r_e/l0)^3 ; + diagonal + 5 % head-room
+	const double q = s->env.r_e / s->env.l0;
+	const double k_mean = (D == 3 ? 4.18879 * q * q * q : 3.14159 * q * q) * 1.05 + 2.0;
+	lim.max_nnz = round_up(static_cast<uint32_t>(lim.max_rows * k_mean), 8);
+	if (lim.max_nnz < row_max + 1) lim.max_nnz = round_up(row_max + 1, 8);
+	// window ~ (2 D - 1 ... 3^(D-1)) columns x (rows + 2 cells of mean occupancy)
+	const double cell = s->env.neighbor_length / s->env.l0;
+	const double occ = (D == 3) ? cell * cell * cell : cell * cell;
+	const double cols = (D == 3) ? 9.0 : 3.0;
+	lim.max_window = round_up(static_cast<uint32_t>(cols * (lim.max_rows + 2.0 * occ) * 1.15) + 32u, 16);
+	if (lim.max_window < row_max + 2 * kMaxRanges) lim.max_window = round_up(row_max + 2 * kMaxRanges, 16);
+	lim.cost_fixed = 12000; lim.cost_per_nnz = 1;
+	if (const char* v = std::getenv("MPS_CG_COST_FIXED")) lim.cost_fixed = static_cast<uint32_t>(std::atoi(v));
+	c.limits = lim;
+	const StreamGeometry g = stream_geometry(lim);
+	const size_t budget = 225u * 1024u;
+	int stages = static_cast<int>((budget - g.fixed_bytes) / g.stage_bytes);
+	if (stages > 8) stages = 8;
+	if (const char* v = std::getenv("MPS_CG_STAGES")) { const int w = std::atoi(v); if (w >= 2 && w <= stages) stages = w; }
+	// every stage must always serve the same consumer group: a group may only wait on barriers it consumes in order
+	// (an mbarrier parity wait cannot tell phase n from phase n + 2)
+	stages = stages / static_cast<int>(kGroups) * static_cast<int>(kGroups);
+	c.stages = stages;
+	// u16 row offsets / columns and the shared memory of one SM bound what can be streamed; otherwise the generic kernel
+	c.chunked = (lim.max_nnz < 65536u) && (lim.max_window < 65536u) && (stages >= 2);
+	if (const char* v = std::getenv("MPS_CG_GENERIC")) { if (std::atoi(v) != 0) c.chunked = false; }
+	return cudaSuccess;
 }
 
 } // namespace mps

@@ -55,10 +55,56 @@ struct DevScalars
 	unsigned long long cg_iterations;
 	double rr0, rr;                 // ||r0||^2, final ||r||^2
 	int cg_converged;
+	int z_final;                    // which of the streaming kernel's {r, p} buffers holds the final residual / direction
 	int error;                      // sticky mps_status raised on the device (cell overflow, CG failure)
 	unsigned int disabled_now;      // particles disabled by the last search
 	unsigned long long active_rows; // PPE rows of the last assembly that are not Dummy / Disabled
+	unsigned long long n_chunks;    // chunks of the last assembly
+	unsigned long long blob_total;  // bytes of all chunk blobs of the last assembly
+	unsigned long long cost_total;  // sum of the chunk cost model (load balance of the CG kernel)
+	unsigned long long grid_barrier; // arrival counter of the CG kernel's grid barrier (zeroed before each launch)
 };
+
+// ---- PPE in "chunk blob" form (what the CG kernel streams, DESIGN.md "CG kernel") ---------------------------------------
+// Rows (slots) are cut into chunks of consecutive rows.  A chunk owns one contiguous, 16-byte aligned byte blob
+//   [ copy of the chunk's descriptor : 128 B ][ val : nnz_pad x f64 ][ lcol : nnz_pad x u16 ][ rowoff : rows_pad x u16 ]
+//                                                            nnz_pad = round_up(nnz, 8), rows_pad = round_up(rows + 1, 8)
+// so that one bulk async copy brings the whole chunk into shared memory.  Columns are 16-bit indices into the chunk's
+// WINDOW: the union of the <= 3 (2-D) / 9 (3-D) contiguous slot ranges that hold every neighbour cell of the chunk's rows
+// (slots are cell-sorted, so the three z-neighbour cells of one (x[,y]) column are one contiguous range).  The CG kernel
+// stages the window of the gathered vectors in shared memory with bulk copies as well.
+constexpr int kMaxRanges = 9;
+struct alignas(16) ChunkDesc
+{
+	uint32_t row_begin;               // first row (slot) of the chunk
+	uint32_t rows;                    // consecutive rows
+	uint32_t nnz;                     // matrix entries of those rows (un-padded)
+	uint32_t nranges;                 // window ranges in use
+	uint64_t blob_off;                // byte offset of the blob (multiple of 16)
+	uint32_t blob_bytes;              // multiple of 16
+	uint32_t window;                  // window entries = sum of range_len (each even)
+	uint32_t range_start[kMaxRanges]; // first staged slot of each range (even => 16-byte aligned doubles)
+	uint16_t range_len[kMaxRanges];   // staged entries (even)
+	uint16_t range_off[kMaxRanges];   // position of the range inside the window
+	int32_t self_off;                 // window position of row_begin: an ACTIVE row r of the chunk sits at self_off + (r - row_begin)
+	uint64_t cost_off;                // exclusive prefix of the chunk cost model (ChunkLimits::cost_*)
+	uint64_t pad_;
+};
+static_assert(sizeof(ChunkDesc) == 128, "one descriptor = one 128-byte bulk copy into the stage");
+static_assert(sizeof(ChunkDesc) % 16 == 0, "descriptors are read with 16-byte loads");
+
+struct ChunkLimits
+{
+	uint32_t max_rows;   // <= 256 (one builder thread partitions one block of 256 rows); = consumer threads / lanes per row
+	uint32_t max_nnz;    // entries per chunk (bounds the blob stage in shared memory; < 65536 for u16 row offsets)
+	uint32_t max_window; // window entries per chunk (bounds the vector stages in shared memory)
+	uint32_t cost_fixed, cost_per_nnz; // load-balance model of one chunk with entries: cost_fixed + cost_per_nnz x entries
+};
+
+__host__ __device__ inline uint32_t round_up8(uint32_t v) { return (v + 7u) & ~7u; }
+constexpr uint32_t kBlobHeader = 128; // the descriptor travels with the blob: one bulk copy per chunk (a bulk copy costs ~420 cycles of
+                                      // the SM's copy engine whatever its size, tools/tma_bench.cu)
+__host__ __device__ inline uint32_t chunk_blob_bytes(uint32_t rows, uint32_t nnz) { return kBlobHeader + round_up8(nnz) * 10u + round_up8(rows + 1u) * 2u; }
 
 template<int D>
 struct Particles

@@ -301,13 +301,20 @@ __global__ void __launch_bounds__(kThreads) k_row_len(uint64_t n, Particles<D> P
 	row_len[i] = len;
 }
 
-// Computer::SetPressurePoissonEquation, Computer.hpp:1145-1328, written straight into the device CSR:
+// Computer::SetPressurePoissonEquation, Computer.hpp:1145-1328, written straight into device memory:
 // row i = [off-diagonals in neighbour-list order ..., diagonal].  Inactive rows (Dummy / Disabled) have length 0 on the
 // device (the reference's identity rows never couple to anything: b = x = 0, Computer.hpp:1195-1202).
-template<int D>
+// CHUNKED = false: plain CSR (row_ptr, col, val).  CHUNKED = true: the chunk-blob form the streaming CG kernel reads
+// (mps_device.cuh): values + 16-bit window-local columns at the row's 16-bit offset inside its chunk's blob.
+struct PpeOut
+{
+	const uint64_t* row_ptr; uint32_t* col; double* val;                                  // CSR
+	const ChunkDesc* desc; const uint32_t* chunk_of_row; unsigned char* blobs;           // chunk blobs
+};
+
+template<int D, bool CHUNKED>
 __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
-	const double* __restrict__ ecs, const uint64_t* __restrict__ row_ptr, uint32_t* __restrict__ col, double* __restrict__ val,
-	double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
+	const double* __restrict__ ecs, PpeOut out, double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
 {
 	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
@@ -325,9 +332,42 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> 
 	b[i] = -env.rho / (n0 * dt) * (speed + ecs[i]);
 	x[i] = P.prs[i];
 
+	// where this row's entries go
+	uint32_t* col = nullptr; double* val = nullptr; uint16_t* lcol = nullptr;
+	uint64_t w = 0;
+	uint32_t rstart[kMaxRanges], rlen[kMaxRanges], roff[kMaxRanges];
+	if (CHUNKED)
+	{
+		const ChunkDesc* d = out.desc + out.chunk_of_row[i];
+		const uint32_t nnz_pad = round_up8(d->nnz);
+		unsigned char* blob = out.blobs + d->blob_off + kBlobHeader;
+		val = reinterpret_cast<double*>(blob);
+		lcol = reinterpret_cast<uint16_t*>(blob + static_cast<uint64_t>(nnz_pad) * 8u);
+		const uint16_t* rowoff = lcol + nnz_pad;
+		w = rowoff[static_cast<uint32_t>(i) - d->row_begin];
+#pragma unroll
+		for (int k = 0; k < kMaxRanges; k++) { rstart[k] = d->range_start[k]; rlen[k] = d->range_len[k]; roff[k] = d->range_off[k]; }
+	}
+	else
+	{
+		col = out.col; val = out.val; w = out.row_ptr[i];
+	}
+	auto put = [&](const uint32_t j, const double a)
+	{
+		if (CHUNKED)
+		{
+			uint32_t l = 0xffffu;
+#pragma unroll
+			for (int k = kMaxRanges - 1; k >= 0; k--) { const uint32_t o = j - rstart[k]; if (o < rlen[k]) l = roff[k] + o; }
+			lcol[w] = static_cast<uint16_t>(l);
+		}
+		else col[w] = j;
+		val[w] = a;
+		w++;
+	};
+
 	// matrix row, Computer.hpp:1246-1327
 	const Vec<D> xi = P.pos[i];
-	uint64_t w = row_ptr[i];
 	const double a_ii = accumulate<D, false, false, true>(i, P, L, nws, env, 0.0,
 		[&](long long j, const Vec<D>& xj, const Vec<D>&, double, uint8_t type) -> double
 		{
@@ -335,13 +375,12 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> 
 			{
 				const double r = dist<D>(xi, xj);
 				const double a_ij = env.ppe_coef / (r * r * r);
-				if (j >= 0) { col[w] = static_cast<uint32_t>(j); val[w] = a_ij; w++; }
+				if (j >= 0) put(static_cast<uint32_t>(j), a_ij);
 				return -a_ij;
 			}
 			return 0.0;
 		});
-	col[w] = static_cast<uint32_t>(i);
-	val[w] = a_ii;
+	put(static_cast<uint32_t>(i), a_ii);
 }
 
 // pressure write-back, Computer.hpp:1076-1097
@@ -625,14 +664,30 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 	CgBuffers& cg = s->cg;
 	MPS_TRY(cg.rowptr.ensure(n + 1, st));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->row_len.p, cg.rowptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
-	// nnz <= neighbour entries + n (every row adds its diagonal): no host round trip needed to size the CSR
-	const uint64_t bound = s->nbr_total + n;
-	MPS_TRY(cg.col.ensure(bound, st)); MPS_TRY(cg.val.ensure(bound, st));
-	MPS_TRY(cg.b.ensure(n, st)); MPS_TRY(cg.x.ensure(n, st)); MPS_TRY(cg.r.ensure(n, st));
-	MPS_TRY(cg.p0.ensure(n, st)); MPS_TRY(cg.p1.ensure(n, st)); MPS_TRY(cg.ap.ensure(n, st));
+	// the streaming kernel stages even-aligned windows: one element of slack behind every vector
+	MPS_TRY(cg.b.ensure(n + 16, st)); MPS_TRY(cg.x.ensure(n + 16, st)); if (!cg.chunked) MPS_TRY(cg.r.ensure(n + 16, st));
+	MPS_TRY(cg.ap.ensure(n + 16, st));
+	if (cg.chunked) { MPS_TRY(cg.z0.ensure(2 * (n + 16), st)); MPS_TRY(cg.z1.ensure(2 * (n + 16), st)); }
+	else { MPS_TRY(cg.p0.ensure(n + 16, st)); MPS_TRY(cg.p1.ensure(n + 16, st)); }
 	cg.n = n; cg.external = false;
+	PpeOut out{};
+	if (cg.chunked)
+	{
+		MPS_TRY(launch_chunk_build(s));
+		out.desc = cg.desc.p; out.chunk_of_row = cg.chunk_of_row.p; out.blobs = cg.blobs.p;
+	}
+	else
+	{
+		// nnz <= neighbour entries + n (every row adds its diagonal): no host round trip needed to size the CSR
+		const uint64_t bound = s->nbr_total + n;
+		MPS_TRY(cg.col.ensure(bound, st)); MPS_TRY(cg.val.ensure(bound, st));
+		out.row_ptr = cg.rowptr.p; out.col = cg.col.p; out.val = cg.val.p;
+	}
 	MPS_TRY(cudaMemsetAsync(&s->d_sc->active_rows, 0, sizeof(unsigned long long), st));
-	k_ppe_fill<D><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, cg.rowptr.p, cg.col.p, cg.val.p, cg.b.p, cg.x.p, s->env, s->d_sc);
+	if (cg.chunked)
+		k_ppe_fill<D, true><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
+	else
+		k_ppe_fill<D, false><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(cudaMemcpyAsync(&s->d_sc->nnz_total, cg.rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
 	return cudaGetLastError();
@@ -712,13 +767,19 @@ template<int D> cudaError_t vec_to_orig(mps_solver* s, int which, double* out)
 	case 0: src = s->cg.x.p; break;
 	case 1: src = s->cg.b.p; break;
 	case 2: src = s->cg.r.p; break;
-	case 3: src = s->cg.p0.p; break;
+	case 3: src = s->cg.p0.p; break; // generic kernel: direction of the last completed iteration is in one of p0 / p1
 	case 4: src = s->cg.ap.p; break;
 	case 5: src = s->ecs.p; break;
 	case 6: src = s->nws.p; break;
 	case 7: src = s->du.p; width = D; stride = s->vec_stride(); break;
 	case 8: src = s->x0.p; width = D; stride = s->vec_stride(); break;
 	default: return cudaErrorInvalidValue;
+	}
+	if (s->cg.chunked && !s->cg.external && (which == 2 || which == 3))
+	{
+		// streaming kernel: {r, p} interleaved; h_sc->z_final (refreshed by the caller) says which buffer is current
+		src = (s->h_sc->z_final ? s->cg.z1.p : s->cg.z0.p) + (which == 3 ? 1 : 0);
+		stride = 2;
 	}
 	if (s->cg.external && which <= 4)
 	{

@@ -55,8 +55,24 @@ struct CgBuffers
 	DevBuf<uint32_t> col;
 	DevBuf<double> val;
 	DevBuf<double> b, x, r, p0, p1, ap;
+	DevBuf<double> z0, z1;   // streaming kernel: {r_i, p_i} interleaved (2 doubles per row), ping-pong
 	DevBuf<double> partials; // 2 x max grid size
 	bool external = false;   // loaded through mps_set_system (not assembled from particles)
+
+	// chunk-blob form of the assembled system (mps_device.cuh, mps_chunk.cu); rowptr above is still produced (row lengths
+	// for inspection, nnz), col / val are only used by externally loaded systems
+	bool chunked = false;    // the assembled system is in chunk-blob form and is solved by the streaming kernel
+	ChunkLimits limits{};
+	int stages = 0;          // shared-memory pipeline depth of the streaming kernel
+	int consumer_warps = 8;  // consumer warps per CTA of the streaming kernel (+ 1 producer warp)
+	int lanes_per_row = 1;   // 1 (2-D: ~21 entries per row) or 4 (3-D: ~57)
+	DevBuf<uint32_t> blk_chunks, blk_bytes, blk_cost, chunk_of_row;
+	DevBuf<uint64_t> chunk_base, blob_base, cost_base;
+	DevBuf<ChunkDesc> desc;
+	DevBuf<unsigned char> blobs;
+	uint64_t desc_cap = 0;
+	DevBuf<unsigned long long> prof; // per-CTA cycle counters of the last streaming solve (mps_get_cg_profile)
+	unsigned prof_blocks = 0;
 };
 
 } // namespace mps
@@ -117,6 +133,7 @@ struct mps_solver
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaEvent_t ev_cg0 = nullptr, ev_cg1 = nullptr; // always-on timing of the CG kernel (resolved at the step's own sync)
 	int cg_max_blocks_per_sm = 0;
+	bool cg_profile = false;
 
 	int vec_stride() const { return env.dim == 2 ? 2 : 4; }
 };
@@ -148,7 +165,10 @@ cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
 // mps_scan.cu
 cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /* n + 1 */, uint64_t n, DevBuf<uint64_t>& tmp, cudaStream_t st,
 	uint64_t* launches);
+// mps_chunk.cu
+cudaError_t launch_chunk_build(mps_solver* s);          // row_len, skey, cell_start -> chunk descriptors + row offsets
 // mps_cg.cu
+cudaError_t cg_configure(mps_solver* s);                // picks chunk limits / pipeline depth for this environment
 cudaError_t launch_cg(mps_solver* s);
 cudaError_t cg_time_iteration(mps_solver* s, int reps, double* mean_ms, double* bytes);
 

@@ -10,7 +10,7 @@ echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 ( time timeout 600 python bench.py --impl reference --steps 5 --warmup 1 ) > gpurun_out/bench_ref.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_cg_solve -s 1 -c 1 -o gpurun_out/prof_cg \
-    python bench.py --workload dambreak2d_250k --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_cg.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_cg_stream -s 3 -c 1 -o gpurun_out/prof_cg \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_cg.log 2>&1
 ls -la gpurun_out
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -5 gpurun_out/bench.log

@@ -73,6 +73,7 @@ typedef struct mps_stats
 	double last_rr0, last_rr;  /* ||r0||^2 and final ||r||^2 of the last solve */
 	uint64_t particles, neighbors, nnz, active_rows; /* sizes of the last step */
 	uint64_t kernel_launches;  /* kernels launched by this library since creation */
+	uint64_t disabled_last;    /* particles disabled (left the grid) by the last neighbour search, Computer.hpp:711-715 */
 	double cg_ms;              /* CUDA-event time of the CG kernel, summed over the steps since the last reset (always on) */
 	double cg_bytes;           /* algorithmic bytes of those solves: sum of iterations x (12 nnz + 92 active rows), SURVEY 8d */
 	double stage_ms[16];       /* accumulated CUDA-event time per stage when stage timing is on (see mps_stage_name) */
@@ -109,6 +110,8 @@ int mps_run_until(mps_handle h, double t_next, uint64_t* steps);
 int mps_run_steps(mps_handle h, uint64_t steps, double* device_ms);
 int mps_get_time(mps_handle h, double* t, double* dt);    /* replaces Environment::T()/Dt(), Environment.hpp:230-242 */
 int mps_set_dt(mps_handle h, double dt, int advance);     /* replaces env.Dt() = dt; env.SetNextT() (test fixtures)   */
+/* the Computer constructor COPIES an Environment whose t / dt may already be set (every gtest fixture does) */
+int mps_set_time(mps_handle h, double t, double dt);
 
 /* ---- single stages (what the upstream gtests reach through `friend`, Computer.hpp:437-460) ------------------------ */
 int mps_search_neighbor(mps_handle h);     /* Computer::SearchNeighbor,              Computer.hpp:698-756 + Grid.hpp */

@@ -35,7 +35,7 @@ class MpsStats(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("cg_iterations", C.c_uint64), ("last_cg_iterations", C.c_uint64),
                 ("last_rr0", C.c_double), ("last_rr", C.c_double),
                 ("particles", C.c_uint64), ("neighbors", C.c_uint64), ("nnz", C.c_uint64), ("active_rows", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
+                ("kernel_launches", C.c_uint64), ("disabled_last", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
 
 
 class MpsError(RuntimeError):
@@ -83,6 +83,7 @@ def load_library():
     sig("mps_run_steps", [vp, u64, pd])
     sig("mps_get_time", [vp, pd, pd])
     sig("mps_set_dt", [vp, dbl, C.c_int])
+    sig("mps_set_time", [vp, dbl, dbl])
     for st in ("search_neighbor", "compute_density", "error_correction", "explicit_forces", "save_x", "set_ppe", "solve_ppe",
                "assign_pressure", "implicit_forces", "pressure_gradient", "dynamic_stabilize"):
         sig("mps_" + st, [vp])

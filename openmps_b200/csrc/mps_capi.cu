@@ -135,6 +135,7 @@ int finish_step(mps_solver* s)
 	s->stats.particles = s->n; s->stats.neighbors = s->nbr_total; s->stats.nnz = s->h_sc->nnz_total;
 	s->nnz_total = s->h_sc->nnz_total;
 	s->stats.active_rows = s->h_sc->active_rows;
+	s->stats.disabled_last = s->h_sc->disabled_now;
 	if (s->n)
 	{
 		// the stream is idle here (sync_scalars), so both events have completed
@@ -385,6 +386,16 @@ int mps_set_dt(mps_handle s, double dt, int advance)
 	return set_dt_device(s, dt, advance, false);
 }
 
+int mps_set_time(mps_handle s, double t, double dt)
+{
+	NEED(s);
+	cudaSetDevice(s->device);
+	s->h_sc->t = t; s->h_sc->dt = dt; // pinned host mirror: stays valid until the copy has run (we synchronise)
+	CU(cudaMemcpyAsync(&s->d_sc->t, &s->h_sc->t, 2 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return MPS_OK;
+}
+
 int mps_get_time(mps_handle s, double* t, double* dt)
 {
 	NEED(s);
@@ -456,6 +467,7 @@ int mps_search_neighbor(mps_handle s)
 	STAGE_PROLOGUE;
 	{ StageTimer t(s, kStSearch); CU(launch_sort_and_search(s)); }
 	int rc = sync_scalars(s); if (rc) return rc;
+	s->stats.disabled_last = s->h_sc->disabled_now;
 	return device_status(s);
 }
 int mps_compute_density(mps_handle s) { STAGE_PROLOGUE; STAGE_NEEDS_SEARCH; StageTimer t(s, kStDensity); CU(launch_density(s, false)); return MPS_OK; }

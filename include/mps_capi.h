@@ -74,6 +74,7 @@ typedef struct mps_stats
 	uint64_t particles, neighbors, nnz, active_rows; /* sizes of the last step */
 	uint64_t kernel_launches;  /* kernels launched by this library since creation */
 	uint64_t disabled_last;    /* particles disabled (left the grid) by the last neighbour search, Computer.hpp:711-715 */
+	uint64_t comm_calls;       /* NCCL collectives / send-recv groups issued since the last reset (0 on one GPU) */
 	double cg_ms;              /* CUDA-event time of the CG kernel, summed over the steps since the last reset (always on) */
 	double cg_bytes;           /* algorithmic bytes of those solves: sum of iterations x (12 nnz + 92 active rows), SURVEY 8d */
 	double stage_ms[16];       /* accumulated CUDA-event time per stage when stage timing is on (see mps_stage_name) */
@@ -139,6 +140,17 @@ int mps_get_vec(mps_handle h, int which, double* out);
 /* load an arbitrary CSR system into ppe.{A,b,x} (the CG known-answer tests, test_ComputerConjugateGradient.cpp:93-107) */
 int mps_set_system(mps_handle h, uint64_t n, const uint64_t* rowptr, const uint32_t* col, const double* val, const double* b, const double* x0);
 int mps_get_solution(mps_handle h, uint64_t n, double* x);
+
+/* ---- multi-GPU (no counterpart in the reference, which is single-process OpenMP) ------------------------------------
+ * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,
+ * a file ...), every rank attaches it to its handle BEFORE the first step and then adds the SAME particles in the same
+ * order.  The particle state is replicated; each rank computes the x-slab [own_first, own_last) of the cell-sorted slots
+ * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu. */
+int mps_comm_unique_id(void* out128);
+int mps_comm_init(mps_handle h, int rank, int nranks, const void* id128);
+int mps_comm_info(mps_handle h, int* rank, int* nranks, uint64_t* own_first, uint64_t* own_last);
+/* the slab arithmetic on its own (host only, needs no GPU): slots [first, last) of `rank` among `nranks` for n particles */
+int mps_partition_range(uint64_t n, int nranks, int rank, uint64_t* first, uint64_t* last);
 
 /* ---- measurement ---------------------------------------------------------------------------------------------------- */
 int mps_set_stage_timing(mps_handle h, int on);   /* CUDA-event timing per stage (adds a sync per stage; off by default) */

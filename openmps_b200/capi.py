@@ -35,7 +35,7 @@ class MpsStats(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("cg_iterations", C.c_uint64), ("last_cg_iterations", C.c_uint64),
                 ("last_rr0", C.c_double), ("last_rr", C.c_double),
                 ("particles", C.c_uint64), ("neighbors", C.c_uint64), ("nnz", C.c_uint64), ("active_rows", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("disabled_last", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
+                ("kernel_launches", C.c_uint64), ("disabled_last", C.c_uint64), ("comm_calls", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
 
 
 class MpsError(RuntimeError):
@@ -101,11 +101,25 @@ def load_library():
     sig("mps_stage_name", [C.c_int], C.c_char_p)
     sig("mps_time_kernel", [vp, C.c_char_p, C.c_int, pd, pd])
     sig("mps_flush_l2", [vp])
+    sig("mps_comm_unique_id", [vp])
+    sig("mps_comm_init", [vp, C.c_int, C.c_int, vp])
+    sig("mps_comm_info", [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64)])
+    sig("mps_partition_range", [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)])
     sig("mps_set_cg_profile", [vp, C.c_int])
     sig("mps_get_cg_profile", [vp, pd])
     sig("mps_get_cg_profile_raw", [vp, vp, u64, C.POINTER(u64)])
     _lib = lib
     return lib
+
+
+def partition_range(n, nranks, rank):
+    """Slots [first, last) that `rank` of `nranks` computes for n particles (pure host arithmetic of the slab decomposition)."""
+    lib = load_library()
+    a, b = C.c_uint64(), C.c_uint64()
+    rc = lib.mps_partition_range(int(n), int(nranks), int(rank), C.byref(a), C.byref(b))
+    if rc != MPS_OK:
+        raise MpsError(rc, "bad partition arguments")
+    return a.value, b.value
 
 
 def _ptr(a):
@@ -309,7 +323,7 @@ class GpuComputer:
             names.append(nm.decode()); k += 1
         return {"steps": st.steps, "cg_iterations": st.cg_iterations, "last_cg_iterations": st.last_cg_iterations,
                 "last_rr0": st.last_rr0, "last_rr": st.last_rr, "particles": st.particles, "neighbors": st.neighbors,
-                "nnz": st.nnz, "active_rows": st.active_rows, "kernel_launches": st.kernel_launches, "cg_ms": st.cg_ms, "cg_bytes": st.cg_bytes,
+                "nnz": st.nnz, "active_rows": st.active_rows, "kernel_launches": st.kernel_launches, "comm_calls": st.comm_calls, "disabled_last": st.disabled_last, "cg_ms": st.cg_ms, "cg_bytes": st.cg_bytes,
                 "stage_ms": {nm: st.stage_ms[i] for i, nm in enumerate(names)},
                 "stage_calls": {nm: st.stage_calls[i] for i, nm in enumerate(names)}}
 
@@ -320,6 +334,26 @@ class GpuComputer:
         ms, by = C.c_double(), C.c_double()
         self._check(self.lib.mps_time_kernel(self.h, name.encode(), reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (call on rank 0, distribute with the launcher's own transport)."""
+        lib = load_library()
+        buf = (C.c_ubyte * 128)()
+        rc = lib.mps_comm_unique_id(buf)
+        if rc != MPS_OK:
+            raise MpsError(rc, "mps_comm_unique_id failed (is libnccl loadable?)")
+        return bytes(buf)
+
+    def attach_comm(self, rank, nranks, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.mps_comm_init(self.h, int(rank), int(nranks), buf))
+
+    def comm_info(self):
+        r, n, a, b = C.c_int(), C.c_int(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.mps_comm_info(self.h, C.byref(r), C.byref(n), C.byref(a), C.byref(b)))
+        return {"rank": r.value, "nranks": n.value, "own": (a.value, b.value)}
 
     def set_cg_profile(self, on):
         self._check(self.lib.mps_set_cg_profile(self.h, 1 if on else 0))

@@ -24,8 +24,16 @@ int fail(mps_solver* s, int code, const std::string& msg)
 	if (s) s->last_error = msg; else g_create_error = msg;
 	return code;
 }
+extern "C" void mps_comm_release(mps_handle s);
+
 int cuda_fail(mps_solver* s, cudaError_t e, const char* where)
 {
+	if (s && !s->comm_error.empty())
+	{
+		const std::string msg = std::string(where) + ": " + s->comm_error;
+		s->comm_error.clear();
+		return fail(s, MPS_NCCL_ERROR, msg);
+	}
 	return fail(s, MPS_CUDA_ERROR, std::string(where) + ": " + cudaGetErrorString(e));
 }
 
@@ -70,8 +78,10 @@ struct StageTimer
 	}
 };
 
-int ensure_particle_capacity(mps_solver* s, uint64_t n)
+int ensure_particle_capacity(mps_solver* s, uint64_t n_exact)
 {
+	// slack: in-place all-gathers move nranks x ceil(n / nranks) elements
+	const uint64_t n = n_exact + 64;
 	cudaStream_t st = s->stream;
 	const uint64_t old = s->n;
 	const int vs = s->vec_stride();
@@ -245,6 +255,9 @@ int mps_destroy(mps_handle s)
 	NEED(s);
 	cudaSetDevice(s->device);
 	cudaStreamSynchronize(s->stream);
+	mps_comm_release(s);
+	s->comm.ext.release(); s->cg.step.release();
+	if (s->cg.h_step) cudaFreeHost(s->cg.h_step);
 	for (int b = 0; b < 2; b++)
 	{
 		s->pos[b].release(); s->vel[b].release(); s->prs[b].release(); s->nden[b].release(); s->type[b].release(); s->orig[b].release();

@@ -230,6 +230,7 @@ struct CgStreamArgs
 	uint32_t stages;
 	int l2_stream;             // blobs do not fit L2: stream them evict_first
 	unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (mps_get_cg_profile), nullptr = off
+	uint64_t own0, own1;       // rows this rank updates ([0, n) on one GPU)
 };
 
 constexpr int kMaxStreamWarps = 17;
@@ -463,13 +464,25 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 	return local;
 }
 
-template<int LPR>
-__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamArgs a)
+// Per-CTA set-up shared by the persistent kernel (one GPU) and the stepwise kernels (one launch per phase, multi-GPU):
+// shared-memory carve-up, barrier initialisation, this CTA's cost-balanced run of chunks and its rows, clamped to the rows
+// the rank owns.
+struct StreamCta
 {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
+	StreamSmem sm;
+	double* red;
+	uint32_t c0, c1, live;
+	uint64_t row0, row1;
+	uint64_t pol_matrix, pol_vector;
+};
+
+template<bool ZERO_ROWS>
+__device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigned char* smem_raw)
+{
 	const uint32_t S = a.stages;
 	const unsigned nthreads = blockDim.x, cwarps = (blockDim.x >> 5) - 1;
-	StreamSmem sm;
+	StreamCta c;
+	StreamSmem& sm = c.sm;
 	sm.base = smem_raw;
 	sm.blob_stage_bytes = a.blob_stage_bytes;
 	sm.window_stage = a.window_stage;
@@ -478,9 +491,9 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	sm.full = reinterpret_cast<uint64_t*>(sm.dring + 2 * kDescBatch);
 	sm.empty = sm.full + S;
 	sm.dfull = sm.empty + S;
-	double* red = reinterpret_cast<double*>(sm.dfull + 2);                  // kMaxStreamWarps + 1
-	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(red + kMaxStreamWarps + 1); // row0, row1
-	uint32_t* ctl = reinterpret_cast<uint32_t*>(ctl64 + 2);                  // c0, c1, live chunks
+	c.red = reinterpret_cast<double*>(sm.dfull + 2);                          // kMaxStreamWarps + 1
+	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(c.red + kMaxStreamWarps + 1); // row0, row1
+	uint32_t* ctl = reinterpret_cast<uint32_t*>(ctl64 + 2);                    // c0, c1, live chunks
 
 	const uint64_t n = a.n;
 	const unsigned nblocks = gridDim.x;
@@ -506,23 +519,75 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 			bound[w] = static_cast<uint32_t>(lo);
 		}
 		ctl[0] = bound[0]; ctl[1] = bound[1]; ctl[2] = 0;
-		ctl64[0] = (bound[0] < nchunks) ? a.desc[bound[0]].row_begin : n;
-		ctl64[1] = (bound[1] < nchunks) ? a.desc[bound[1]].row_begin : n;
+		uint64_t r0 = (bound[0] < nchunks) ? a.desc[bound[0]].row_begin : n;
+		uint64_t r1 = (bound[1] < nchunks) ? a.desc[bound[1]].row_begin : n;
+		// rows of other ranks (multi-GPU) are never updated here
+		r0 = r0 < a.own0 ? a.own0 : (r0 > a.own1 ? a.own1 : r0);
+		r1 = r1 < a.own0 ? a.own0 : (r1 > a.own1 ? a.own1 : r1);
+		ctl64[0] = r0; ctl64[1] = r1;
 	}
 	__syncthreads();
-	const uint32_t c0 = ctl[0], c1 = ctl[1];
-	const uint64_t row0 = ctl64[0], row1 = ctl64[1];
+	c.c0 = ctl[0]; c.c1 = ctl[1];
+	c.row0 = ctl64[0]; c.row1 = ctl64[1];
 	{
 		// chunks with entries (the others are skipped by every phase) ; rows of this CTA start from zero everywhere
 		uint32_t mine = 0;
-		for (uint32_t c = c0 + threadIdx.x; c < c1; c += nthreads) mine += (a.desc[c].nnz != 0) ? 1u : 0u;
+		for (uint32_t k = c.c0 + threadIdx.x; k < c.c1; k += nthreads) mine += (a.desc[k].nnz != 0) ? 1u : 0u;
 		if (mine) atomicAdd(&ctl[2], mine);
-		for (uint64_t i = row0 + threadIdx.x; i < row1; i += nthreads) { a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0; }
+		if (ZERO_ROWS)
+			for (uint64_t i = c.row0 + threadIdx.x; i < c.row1; i += nthreads) { a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0; }
 	}
 	__syncthreads();
-	const uint32_t live = ctl[2];
-	const uint64_t pol_matrix = a.l2_stream ? async::policy_evict_first() : async::policy_evict_normal();
-	const uint64_t pol_vector = a.l2_stream ? async::policy_evict_last() : async::policy_evict_normal();
+	c.live = ctl[2];
+	c.pol_matrix = a.l2_stream ? async::policy_evict_first() : async::policy_evict_normal();
+	c.pol_vector = a.l2_stream ? async::policy_evict_last() : async::policy_evict_normal();
+	return c;
+}
+
+// phase 2 over rows [row0, row1): x += alpha p ; r -= alpha Ap ; returns this thread's share of r.r (4 independent rows in flight)
+__device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint64_t row0, const uint64_t row1, const double alpha,
+	const double2* __restrict__ zprev, double2* __restrict__ zcur)
+{
+	const unsigned nthreads = blockDim.x;
+	double local = 0.0;
+	for (uint64_t base = row0 + threadIdx.x; base < row1; base += 4ull * nthreads)
+	{
+		double pv[4], xv[4], av[4], rv[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+		{
+			const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
+			const bool on = i < row1;
+			pv[q] = on ? zcur[i].y : 0.0; xv[q] = on ? a.x[i] : 0.0; av[q] = on ? a.ap[i] : 0.0; rv[q] = on ? zprev[i].x : 0.0;
+		}
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+		{
+			const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
+			if (i < row1)
+			{
+				a.x[i] = fma(alpha, pv[q], xv[q]);
+				const double ri = fma(-alpha, av[q], rv[q]);
+				zcur[i].x = ri;
+				local = fma(ri, ri, local);
+			}
+		}
+	}
+	return local;
+}
+
+template<int LPR>
+__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const StreamCta cta = stream_setup<true>(a, smem_raw);
+	const StreamSmem& sm = cta.sm;
+	double* red = cta.red;
+	const uint32_t c0 = cta.c0, c1 = cta.c1, live = cta.live;
+	const uint64_t row0 = cta.row0, row1 = cta.row1;
+	const uint64_t pol_matrix = cta.pol_matrix, pol_vector = cta.pol_vector;
+	const uint64_t n = a.n;
+	const unsigned nblocks = gridDim.x;
 	double* part0 = a.partials;
 	double* part1 = a.partials + nblocks;
 	unsigned long long bar_target = 0;
@@ -556,31 +621,8 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 		const double pAp = grid_sum_n(part1, nblocks, red);
 		const double alpha = rr / pAp;
 
-		// ---- phase 2 over this CTA's own rows: x += alpha p ; r -= alpha Ap ; r.r (4 independent rows in flight per thread) ----
-		local = 0.0;
-		for (uint64_t base = row0 + threadIdx.x; base < row1; base += 4ull * nthreads)
-		{
-			double pv[4], xv[4], av[4], rv[4];
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-			{
-				const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
-				const bool on = i < row1;
-				pv[q] = on ? zcur[i].y : 0.0; xv[q] = on ? a.x[i] : 0.0; av[q] = on ? a.ap[i] : 0.0; rv[q] = on ? zprev[i].x : 0.0;
-			}
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-			{
-				const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
-				if (i < row1)
-				{
-					a.x[i] = fma(alpha, pv[q], xv[q]);
-					const double ri = fma(-alpha, av[q], rv[q]);
-					zcur[i].x = ri;
-					local = fma(ri, ri, local);
-				}
-			}
-		}
+		// ---- phase 2 over this CTA's own rows: x += alpha p ; r -= alpha Ap ; r.r ----
+		local = update_rows(a, row0, row1, alpha, zprev, zcur);
 		local = block_sum_n(local, red);
 		if (threadIdx.x == 0) part0[blockIdx.x] = local;
 		const long long t3 = prof_on ? clock64() : 0;
@@ -616,6 +658,62 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	}
 }
 
+// ---- stepwise form for multi-GPU runs: one launch per phase, the scalars of the recurrence live in device memory so that
+//      NCCL all-reduces can run between the launches (mps_comm.cu drives the loop) ----
+template<int LPR, int PHASE> // 0: r0 = b - A x ; 1: p, Ap, p.Ap ; 2: x, r, r.r
+__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_step(CgStreamArgs a, CgStepScalars* st)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const StreamCta cta = (PHASE == 0) ? stream_setup<true>(a, smem_raw) : stream_setup<false>(a, smem_raw);
+	uint32_t it = 0, dseq = 0;
+	double2* zprev = st->zcur_is_1 ? a.z0 : a.z1;
+	double2* zcur = st->zcur_is_1 ? a.z1 : a.z0;
+	double local = 0.0;
+	if (PHASE == 0) local = spmv_phase<LPR, false>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, 0.0, nullptr, a.z0, cta.pol_matrix, cta.pol_vector);
+	if (PHASE == 1) local = spmv_phase<LPR, true>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, st->beta, zprev, zcur, cta.pol_matrix, cta.pol_vector);
+	if (PHASE == 2) local = update_rows(a, cta.row0, cta.row1, st->rr / st->pAp, zprev, zcur);
+	local = block_sum_n(local, cta.red);
+	if (threadIdx.x == 0) a.partials[blockIdx.x] = local;
+}
+
+// fixed-order sum of the per-CTA partials -> *dst (one block)
+__global__ void __launch_bounds__(256) k_cg_reduce(const double* __restrict__ partials, unsigned nblocks, double* dst)
+{
+	__shared__ double red[256 / 32 + 1];
+	double v = 0.0;
+	for (unsigned k = threadIdx.x; k < nblocks; k += 256) v += partials[k];
+	v = block_sum_n(v, red);
+	if (threadIdx.x == 0) *dst = v;
+}
+
+// scalar recurrences between the phases (one thread) — Computer.hpp:1386-1417
+__global__ void k_cg_after_init(CgStepScalars* st, double eps)
+{
+	st->rr0 = st->rr;
+	st->tol = st->rr * eps * eps;
+	st->converged = (st->tol == 0) ? 1 : 0;
+	st->beta = 0.0;
+	st->iter = 0;
+	st->zcur_is_1 = 1; // z0 = {r0, 0} is "previous"
+}
+__global__ void k_cg_after_iter(CgStepScalars* st)
+{
+	st->iter += 1;
+	st->converged = (st->rr_new < st->tol) ? 1 : 0;
+	if (!st->converged) st->beta = st->rr_new / st->rr;
+	st->zcur_is_1 ^= 1;
+	st->rr = st->rr_new;
+}
+__global__ void k_cg_finish(const CgStepScalars* st, DevScalars* sc)
+{
+	sc->z_final = st->zcur_is_1 ? 0 : 1; // the buffer written last is the current "previous"
+	sc->cg_iterations = st->iter;
+	sc->rr0 = st->rr0;
+	sc->rr = st->rr;
+	sc->cg_converged = st->converged;
+	if (!st->converged) atomicMax(&sc->error, static_cast<int>(MPS_CG_NOT_CONVERGED));
+}
+
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 struct StreamGeometry
@@ -634,43 +732,85 @@ StreamGeometry stream_geometry(const ChunkLimits& lim)
 	return g;
 }
 
-template<int LPR>
-cudaError_t launch_stream(mps_solver* s)
+struct StreamLaunch
+{
+	CgStreamArgs a;
+	size_t smem_bytes;
+	unsigned grid;
+	int threads;
+};
+
+cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 {
 	CgBuffers& c = s->cg;
 	const StreamGeometry g = stream_geometry(c.limits);
-	const size_t smem_bytes = static_cast<size_t>(c.stages) * g.stage_bytes + g.fixed_bytes;
-	const int threads = (c.consumer_warps + 1) * 32;
-	cudaError_t e = cudaFuncSetAttribute(k_cg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+	L.smem_bytes = static_cast<size_t>(c.stages) * g.stage_bytes + g.fixed_bytes;
+	L.threads = (c.consumer_warps + 1) * 32;
+	L.grid = static_cast<unsigned>(s->sm_count); // one CTA per SM: the ring wants the whole shared memory
+	cudaError_t e = c.partials.ensure(2ull * L.grid + 8, s->stream);
 	if (e != cudaSuccess) return e;
-	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_stream<LPR>, threads, smem_bytes);
-	if (e != cudaSuccess) return e;
-	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-	const unsigned grid = static_cast<unsigned>(s->sm_count); // one CTA per SM: the ring wants the whole shared memory
-	e = c.partials.ensure(2ull * grid, s->stream);
-	if (e != cudaSuccess) return e;
-	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
-	if (e != cudaSuccess) return e;
-	CgStreamArgs a;
+	CgStreamArgs& a = L.a;
 	a.n = c.n; a.desc = c.desc.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
 	a.ap = c.ap.p; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
 	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
 	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
-	a.l2_stream = ((s->nbr_total + c.n) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
+	a.l2_stream = ((s->nbr_total + (s->own1() - s->own0())) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
 	a.prof = nullptr;
+	a.own0 = s->own0(); a.own1 = s->own1();
+	return cudaSuccess;
+}
+
+template<int LPR>
+cudaError_t launch_stream(mps_solver* s)
+{
+	CgBuffers& c = s->cg;
+	StreamLaunch L;
+	cudaError_t e = prepare_stream(s, L);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(k_cg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_stream<LPR>, L.threads, L.smem_bytes);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
+	if (e != cudaSuccess) return e;
 	if (s->cg_profile)
 	{
-		e = c.prof.ensure(8ull * grid, s->stream);
+		e = c.prof.ensure(8ull * L.grid, s->stream);
 		if (e != cudaSuccess) return e;
-		e = cudaMemsetAsync(c.prof.p, 0, 8ull * grid * sizeof(unsigned long long), s->stream);
+		e = cudaMemsetAsync(c.prof.p, 0, 8ull * L.grid * sizeof(unsigned long long), s->stream);
 		if (e != cudaSuccess) return e;
-		a.prof = c.prof.p;
-		c.prof_blocks = grid;
+		L.a.prof = c.prof.p;
+		c.prof_blocks = L.grid;
 	}
-	void* params[] = { &a };
+	void* params[] = { &L.a };
 	s->stats.kernel_launches += 1;
-	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR>), dim3(grid), dim3(threads), params, smem_bytes, s->stream);
+	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+}
+
+template<int LPR, int PHASE>
+cudaError_t launch_step_phase(mps_solver* s, CgStepScalars* st)
+{
+	StreamLaunch L;
+	cudaError_t e = prepare_stream(s, L);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(k_cg_step<LPR, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	if (e != cudaSuccess) return e;
+	k_cg_step<LPR, PHASE><<<L.grid, L.threads, L.smem_bytes, s->stream>>>(L.a, st);
+	s->stats.kernel_launches += 1;
+	return cudaGetLastError();
+}
+
+template<int LPR>
+cudaError_t launch_step_lpr(mps_solver* s, int phase, CgStepScalars* st)
+{
+	switch (phase)
+	{
+	case 0: return launch_step_phase<LPR, 0>(s, st);
+	case 1: return launch_step_phase<LPR, 1>(s, st);
+	default: return launch_step_phase<LPR, 2>(s, st);
+	}
 }
 
 template<int LPR>
@@ -701,6 +841,7 @@ cudaError_t launch_cg(mps_solver* s)
 		// an empty system is converged by definition (residual0 == 0)
 		return cudaSuccess;
 	}
+	if (c.chunked && !c.external && s->comm.on) return comm_cg_solve(s);
 	if (c.chunked && !c.external)
 	{
 		switch (c.lanes_per_row)
@@ -719,6 +860,32 @@ cudaError_t launch_cg(mps_solver* s)
 	const int lpr = (s->env.dim == 3 && !c.external) ? 16 : 8;
 	const unsigned want = blocks_for(c.n * static_cast<uint64_t>(lpr), kCgThreads);
 	return lpr == 16 ? launch_lpr<16>(s, args, want) : launch_lpr<8>(s, args, want);
+}
+
+// ---- stepwise interface used by the multi-GPU driver loop (mps_comm.cu) -------------------------------------------------
+cudaError_t launch_cg_step(mps_solver* s, int phase, CgStepScalars* st)
+{
+	switch (s->cg.lanes_per_row)
+	{
+	case 1: return launch_step_lpr<1>(s, phase, st);
+	case 2: return launch_step_lpr<2>(s, phase, st);
+	case 4: return launch_step_lpr<4>(s, phase, st);
+	default: return launch_step_lpr<8>(s, phase, st);
+	}
+}
+cudaError_t launch_cg_reduce(mps_solver* s, double* dst)
+{
+	k_cg_reduce<<<1, 256, 0, s->stream>>>(s->cg.partials.p, static_cast<unsigned>(s->sm_count), dst);
+	s->stats.kernel_launches += 1;
+	return cudaGetLastError();
+}
+cudaError_t launch_cg_scalars(mps_solver* s, int which, CgStepScalars* st)
+{
+	if (which == 0) k_cg_after_init<<<1, 1, 0, s->stream>>>(st, s->env.eps);
+	else if (which == 1) k_cg_after_iter<<<1, 1, 0, s->stream>>>(st);
+	else k_cg_finish<<<1, 1, 0, s->stream>>>(st, s->d_sc);
+	s->stats.kernel_launches += 1;
+	return cudaGetLastError();
 }
 
 // Chunk limits for this environment.  Rows per chunk = consumer threads / lanes per row (every consumer sub-warp owns one row

@@ -1,0 +1,268 @@
+// mps_comm.cu — multi-GPU: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// Decomposition (DESIGN.md "multi-GPU"): the cell-sorted slot order is x-major, so a contiguous range of slots IS an
+// x-slab of the domain, and equal slot counts give equal particle counts per rank whatever the shape of the fluid (the
+// dam break starts in the left quarter of the tank; equal-width slabs would idle most GPUs — SURVEY H9).  Every rank
+// keeps the whole particle state (a few hundred bytes per particle) but COMPUTES only its slab: neighbour lists,
+// gather stages, PPE rows and the CG rows of its slots; what grows with the problem — neighbour list and matrix — is
+// therefore partitioned.  Exchanges, all on the solver's stream:
+//   * after the stages that move particles or set pressures: in-place ncclAllGather of the fields neighbours read
+//     (x, u after the explicit move, the pressure gradient and the stabiliser; P after the solve).  Re-sorting the
+//     replicated state every step replaces particle migration.
+//   * per CG iteration: the {r, p} values of the slab's rim that the neighbour's windows reach (ncclSend/ncclRecv with
+//     the two adjacent ranks, contiguous slot ranges, no packing) and two ncclAllReduce of one double (p.Ap, r.r).
+// The reference has nothing to compare with here (single process, OpenMP); parity is 1 GPU vs N GPUs on the same input.
+//
+// NCCL is loaded with dlopen so that the library neither links against a particular libnccl nor fights the copy that
+// PyTorch bundles when both live in one process.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <nccl.h>
+
+#include "mps_solver.h"
+
+namespace mps {
+namespace {
+
+struct Nccl
+{
+	void* lib = nullptr;
+	decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+	decltype(&ncclCommInitRank) CommInitRank = nullptr;
+	decltype(&ncclCommDestroy) CommDestroy = nullptr;
+	decltype(&ncclAllReduce) AllReduce = nullptr;
+	decltype(&ncclAllGather) AllGather = nullptr;
+	decltype(&ncclSend) Send = nullptr;
+	decltype(&ncclRecv) Recv = nullptr;
+	decltype(&ncclGroupStart) GroupStart = nullptr;
+	decltype(&ncclGroupEnd) GroupEnd = nullptr;
+	decltype(&ncclGetErrorString) GetErrorString = nullptr;
+	std::string error;
+
+	bool load()
+	{
+		if (lib) return true;
+		for (const char* name : { "libnccl.so.2", "libnccl.so" })
+		{
+			lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (lib) break;
+		}
+		if (!lib) { error = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define MPS_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(lib, #sym)); if (!field) { error = "libnccl lacks " #sym; return false; }
+		MPS_SYM(GetUniqueId, ncclGetUniqueId) MPS_SYM(CommInitRank, ncclCommInitRank) MPS_SYM(CommDestroy, ncclCommDestroy)
+		MPS_SYM(AllReduce, ncclAllReduce) MPS_SYM(AllGather, ncclAllGather) MPS_SYM(Send, ncclSend) MPS_SYM(Recv, ncclRecv)
+		MPS_SYM(GroupStart, ncclGroupStart) MPS_SYM(GroupEnd, ncclGroupEnd) MPS_SYM(GetErrorString, ncclGetErrorString)
+#undef MPS_SYM
+		return true;
+	}
+};
+
+Nccl g_nccl;
+
+#define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
+#define MPS_NCCL(s, expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) { (s)->comm_error = std::string(#expr ": ") + g_nccl.GetErrorString(r_); return cudaErrorUnknown; } } while (0)
+
+inline ncclComm_t comm_of(mps_solver* s) { return static_cast<ncclComm_t>(s->comm.nccl); }
+
+// extent of the slots this rank's windows reach: min range start / max range end over its chunks with entries
+__global__ void k_halo_extent(const ChunkDesc* __restrict__ desc, const DevScalars* __restrict__ sc, unsigned long long* ext)
+{
+	const unsigned long long nchunks = sc->n_chunks;
+	unsigned long long lo = ~0ull, hi = 0;
+	for (unsigned long long c = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks; c += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+	{
+		const ChunkDesc& d = desc[c];
+		if (d.nnz == 0) continue;
+		for (uint32_t q = 0; q < d.nranges; q++)
+		{
+			const unsigned long long b = d.range_start[q], e = b + d.range_len[q];
+			if (b < lo) lo = b;
+			if (e > hi) hi = e;
+		}
+	}
+	if (lo != ~0ull) { atomicMin(&ext[0], lo); atomicMax(&ext[1], hi); }
+}
+
+struct Slab { uint64_t b, e; };
+inline Slab slab_of(const mps_solver* s, int rank)
+{
+	const uint64_t m = s->slab();
+	uint64_t b = static_cast<uint64_t>(rank) * m, e = b + m;
+	if (b > s->n) b = s->n;
+	if (e > s->n) e = s->n;
+	return Slab{ b, e };
+}
+
+// rim exchange of one {r, p} buffer with the two adjacent ranks (host copies of all extents in `ext`)
+cudaError_t halo_exchange(mps_solver* s, double* z, const std::vector<unsigned long long>& ext)
+{
+	const int k = s->comm.rank, R = s->comm.nranks;
+	const Slab me = slab_of(s, k);
+	auto clampu = [](uint64_t v, uint64_t lo, uint64_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+	MPS_NCCL(s, g_nccl.GroupStart());
+	if (k > 0)
+	{
+		const Slab left = slab_of(s, k - 1);
+		// the left rank reads my rows [me.b, ext_hi(left)); I read its rows [ext_lo(me), me.b)
+		const uint64_t send_e = clampu(ext[2 * (k - 1) + 1], me.b, me.e);
+		if (send_e > me.b) MPS_NCCL(s, g_nccl.Send(z + 2 * me.b, 2 * (send_e - me.b), ncclDouble, k - 1, comm_of(s), s->stream));
+		const uint64_t recv_b = clampu(ext[2 * k], left.b, me.b);
+		if (recv_b < me.b) MPS_NCCL(s, g_nccl.Recv(z + 2 * recv_b, 2 * (me.b - recv_b), ncclDouble, k - 1, comm_of(s), s->stream));
+	}
+	if (k + 1 < R)
+	{
+		const Slab right = slab_of(s, k + 1);
+		const uint64_t send_b = clampu(ext[2 * (k + 1)], me.b, me.e);
+		if (send_b < me.e) MPS_NCCL(s, g_nccl.Send(z + 2 * send_b, 2 * (me.e - send_b), ncclDouble, k + 1, comm_of(s), s->stream));
+		const uint64_t recv_e = clampu(ext[2 * k + 1], me.e, right.e);
+		if (recv_e > me.e) MPS_NCCL(s, g_nccl.Recv(z + 2 * me.e, 2 * (recv_e - me.e), ncclDouble, k + 1, comm_of(s), s->stream));
+	}
+	MPS_NCCL(s, g_nccl.GroupEnd());
+	return cudaSuccess;
+}
+
+} // namespace
+
+cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden)
+{
+	if (!s->comm.on || s->n == 0) return cudaSuccess;
+	const uint64_t m = s->slab();
+	const int vs = s->vec_stride();
+	const int k = s->comm.rank;
+	if (pos) { double* p = s->pos[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
+	if (vel) { double* p = s->vel[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
+	if (prs) { double* p = s->prs[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
+	if (nden) { double* p = s->nden[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
+	s->stats.comm_calls += (pos ? 1 : 0) + (vel ? 1 : 0) + (prs ? 1 : 0) + (nden ? 1 : 0);
+	return cudaSuccess;
+}
+
+// Computer::SolvePressurePoissonEquation (Computer.hpp:1359-1429) across ranks: the same CG, the same stopping rule; one
+// launch per phase so that the dot products can be all-reduced and the rim of {r, p} exchanged between them.
+cudaError_t comm_cg_solve(mps_solver* s)
+{
+	CgBuffers& c = s->cg;
+	cudaStream_t st = s->stream;
+	const int R = s->comm.nranks;
+	MPS_TRY(c.step.ensure(1, st));
+	if (!c.h_step) MPS_TRY(cudaMallocHost(&c.h_step, sizeof(CgStepScalars)));
+	MPS_TRY(cudaMemsetAsync(c.step.p, 0, sizeof(CgStepScalars), st));
+
+	// halo extents of every rank (once per solve: the chunks were rebuilt by this step's assembly)
+	MPS_TRY(s->comm.ext.ensure(2ull * R + 2, st));
+	unsigned long long* ext_local = s->comm.ext.p + 2ull * R;
+	const unsigned long long init[2] = { s->own0(), s->own1() };
+	MPS_TRY(cudaMemcpyAsync(ext_local, init, sizeof(init), cudaMemcpyHostToDevice, st));
+	k_halo_extent<<<64, 256, 0, st>>>(c.desc.p, s->d_sc, ext_local);
+	s->stats.kernel_launches += 1;
+	MPS_NCCL(s, g_nccl.AllGather(ext_local, s->comm.ext.p, 2, ncclUint64, comm_of(s), st));
+	std::vector<unsigned long long> ext(2ull * R);
+	MPS_TRY(cudaMemcpyAsync(ext.data(), s->comm.ext.p, 2ull * R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	MPS_TRY(cudaStreamSynchronize(st));
+	for (int k = 0; k < R; k++)
+	{
+		// a window must not reach past the adjacent slab (slabs thinner than one cell column are not supported)
+		const uint64_t lo_ok = (k > 0) ? static_cast<uint64_t>(k - 1) * s->slab() : 0;
+		const uint64_t hi_ok = (k + 1 < R) ? std::min<uint64_t>(static_cast<uint64_t>(k + 2) * s->slab(), s->n) : s->n;
+		if (ext[2 * k] < lo_ok || ext[2 * k + 1] > hi_ok + 1 /* window ends are rounded up to even */) { s->comm_error = "slab thinner than the neighbour stencil: use fewer GPUs for this problem"; return cudaErrorUnknown; }
+	}
+
+	double* z0 = c.z0.p;
+	double* z1 = c.z1.p;
+	CgStepScalars* d = c.step.p;
+	// r0 = b - A x
+	MPS_TRY(launch_cg_step(s, 0, d));
+	MPS_TRY(launch_cg_reduce(s, &d->rr));
+	MPS_NCCL(s, g_nccl.AllReduce(&d->rr, &d->rr, 1, ncclDouble, ncclSum, comm_of(s), st));
+	MPS_TRY(launch_cg_scalars(s, 0, d));
+	MPS_TRY(halo_exchange(s, z0, ext));
+	int zcur_is_1 = 1;
+	const uint64_t max_iter = c.n;
+	uint64_t iter = 0;
+	for (;;)
+	{
+		MPS_TRY(cudaMemcpyAsync(c.h_step, d, sizeof(CgStepScalars), cudaMemcpyDeviceToHost, st));
+		MPS_TRY(cudaStreamSynchronize(st));
+		if (c.h_step->converged || iter >= max_iter) break;
+		MPS_TRY(launch_cg_step(s, 1, d));
+		MPS_TRY(launch_cg_reduce(s, &d->pAp));
+		MPS_NCCL(s, g_nccl.AllReduce(&d->pAp, &d->pAp, 1, ncclDouble, ncclSum, comm_of(s), st));
+		MPS_TRY(launch_cg_step(s, 2, d));
+		MPS_TRY(launch_cg_reduce(s, &d->rr_new));
+		MPS_NCCL(s, g_nccl.AllReduce(&d->rr_new, &d->rr_new, 1, ncclDouble, ncclSum, comm_of(s), st));
+		MPS_TRY(launch_cg_scalars(s, 1, d));
+		MPS_TRY(halo_exchange(s, zcur_is_1 ? z1 : z0, ext)); // the buffer this iteration wrote is the next "previous"
+		zcur_is_1 ^= 1;
+		iter++;
+		s->stats.comm_calls += 4;
+	}
+	MPS_TRY(launch_cg_scalars(s, 2, d));
+	return cudaGetLastError();
+}
+
+} // namespace mps
+
+using namespace mps;
+
+extern "C" {
+
+int mps_comm_unique_id(void* out128)
+{
+	if (!out128) return MPS_BAD_ARG;
+	if (!g_nccl.load()) return MPS_NCCL_ERROR;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) return MPS_NCCL_ERROR;
+	std::memcpy(out128, &id, sizeof(id));
+	return MPS_OK;
+}
+
+int mps_comm_init(mps_handle s, int rank, int nranks, const void* id128)
+{
+	if (!s || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return MPS_BAD_ARG;
+	if (s->n != 0 && s->searched) { s->last_error = "attach the communicator before the first step"; return MPS_BAD_ARG; }
+	if (nranks == 1) { s->comm.on = false; return MPS_OK; }
+	if (!g_nccl.load()) { s->last_error = g_nccl.error; return MPS_NCCL_ERROR; }
+	cudaSetDevice(s->device);
+	ncclUniqueId id;
+	std::memcpy(&id, id128, sizeof(id));
+	ncclComm_t comm = nullptr;
+	const ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+	if (r != ncclSuccess) { s->last_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return MPS_NCCL_ERROR; }
+	s->comm.nccl = comm; s->comm.rank = rank; s->comm.nranks = nranks; s->comm.on = true;
+	return MPS_OK;
+}
+
+int mps_comm_info(mps_handle s, int* rank, int* nranks, uint64_t* own_first, uint64_t* own_last)
+{
+	if (!s) return MPS_BAD_ARG;
+	if (rank) *rank = s->comm.rank;
+	if (nranks) *nranks = s->comm.on ? s->comm.nranks : 1;
+	if (own_first) *own_first = s->own0();
+	if (own_last) *own_last = s->own1();
+	return MPS_OK;
+}
+
+// pure arithmetic of the slab decomposition (no GPU needed): slots [first, last) of `rank` among `nranks` for n particles
+int mps_partition_range(uint64_t n, int nranks, int rank, uint64_t* first, uint64_t* last)
+{
+	if (nranks < 1 || rank < 0 || rank >= nranks || !first || !last) return MPS_BAD_ARG;
+	const uint64_t m = (n + static_cast<uint64_t>(nranks) - 1) / static_cast<uint64_t>(nranks);
+	uint64_t b = static_cast<uint64_t>(rank) * m, e = b + m;
+	if (b > n) b = n;
+	if (e > n) e = n;
+	*first = b; *last = e;
+	return MPS_OK;
+}
+
+void mps_comm_release(mps_handle s)
+{
+	if (s && s->comm.nccl && g_nccl.CommDestroy) { g_nccl.CommDestroy(static_cast<ncclComm_t>(s->comm.nccl)); s->comm.nccl = nullptr; s->comm.on = false; }
+}
+
+} // extern "C"

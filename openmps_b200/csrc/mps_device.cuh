@@ -106,6 +106,15 @@ constexpr uint32_t kBlobHeader = 128; // the descriptor travels with the blob: o
                                       // the SM's copy engine whatever its size, tools/tma_bench.cu)
 __host__ __device__ inline uint32_t chunk_blob_bytes(uint32_t rows, uint32_t nnz) { return kBlobHeader + round_up8(nnz) * 10u + round_up8(rows + 1u) * 2u; }
 
+// scalars of the CG recurrence when the solve runs as one launch per phase (multi-GPU, mps_comm.cu)
+struct CgStepScalars
+{
+	double rr, pAp, rr_new, beta, tol, rr0;
+	unsigned long long iter;
+	int converged;
+	int zcur_is_1;
+};
+
 template<int D>
 struct Particles
 {

@@ -121,10 +121,10 @@ template<int D> __device__ __forceinline__ double dist(const Vec<D>& a, const Ve
 // (in-range, non-Dummy neighbours + the diagonal) for the second call of the step, and saves originalX (SaveX,
 // Computer.hpp:1025-1039) — both read exactly the data this pass has in registers anyway.
 template<int D, bool COUNT_ROWS>
-__global__ void __launch_bounds__(kThreads) k_density(uint64_t n, Particles<D> P, Lists L, double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_density(uint64_t first, uint64_t n, Particles<D> P, Lists L, double* __restrict__ nws,
 	uint32_t* __restrict__ row_len, Vec<D>* __restrict__ x0, EnvConst env)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	const double n0 = env.n0;
@@ -178,10 +178,10 @@ __device__ __forceinline__ double dndt(const uint64_t i, const Particles<D>& P, 
 
 // Computer::ComputeErrorCorrection, Computer.hpp:877-910
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_ecs(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_ecs(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	double* __restrict__ ecs, EnvConst env)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	if ((t != kDummy) && (t != kDisabled))
@@ -203,10 +203,10 @@ __global__ void __launch_bounds__(1) k_dndt_one(uint64_t orig_id, const uint32_t
 
 // Computer::ComputeExplicitForces, first loop, Computer.hpp:937-990: acceleration of fluid particles into `a` (= du)
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_explicit_accel(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_explicit_accel(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	Vec<D>* __restrict__ a, EnvConst env)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	if (P.type[i] != kFluid) return;
 	const Vec<D> xi = P.pos[i], ui = P.vel[i];
@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(kThreads) k_explicit_accel(uint64_t n, Particl
 
 // Computer::ComputeExplicitForces, second loop, Computer.hpp:996-1020
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_explicit_move(uint64_t n, Particles<D> P, const Vec<D>* __restrict__ a,
+__global__ void __launch_bounds__(kThreads) k_explicit_move(uint64_t first, uint64_t n, Particles<D> P, const Vec<D>* __restrict__ a,
 	const Vec<D>* __restrict__ wall /* original order */, const DevScalars* __restrict__ sc)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const double dt = sc->dt;
 	Vec<D> x = P.pos[i], u = P.vel[i];
@@ -281,9 +281,9 @@ __global__ void __launch_bounds__(kThreads) k_save_x(uint64_t n, Particles<D> P,
 
 // PPE row lengths for the stage-level API (the step gets them from k_density<COUNT_ROWS>)
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_row_len(uint64_t n, Particles<D> P, Lists L, uint32_t* __restrict__ row_len, EnvConst env)
+__global__ void __launch_bounds__(kThreads) k_row_len(uint64_t first, uint64_t n, Particles<D> P, Lists L, uint32_t* __restrict__ row_len, EnvConst env)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	uint32_t len = 0;
@@ -313,10 +313,10 @@ struct PpeOut
 };
 
 template<int D, bool CHUNKED>
-__global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	const double* __restrict__ ecs, PpeOut out, double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	if ((t == kDummy) || (t == kDisabled))
@@ -383,11 +383,23 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t n, Particles<D> 
 	put(static_cast<uint32_t>(i), a_ii);
 }
 
-// pressure write-back, Computer.hpp:1076-1097
+// multi-rank only: right-hand side 0 and initial guess x = P (Computer.hpp:1195-1220) for EVERY row; the owners then
+// overwrite their rows in k_ppe_fill.  Rows of other ranks are only ever read as columns.
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_assign_pressure(uint64_t n, Particles<D> P, const double* __restrict__ x)
+__global__ void __launch_bounds__(kThreads) k_ppe_guess(uint64_t n, Particles<D> P, double* __restrict__ b, double* __restrict__ x)
 {
 	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	if (i >= n) return;
+	const uint8_t t = P.type[i];
+	b[i] = 0;
+	x[i] = ((t == kDummy) || (t == kDisabled)) ? 0.0 : P.prs[i];
+}
+
+// pressure write-back, Computer.hpp:1076-1097
+template<int D>
+__global__ void __launch_bounds__(kThreads) k_assign_pressure(uint64_t first, uint64_t n, Particles<D> P, const double* __restrict__ x)
+{
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	if ((t != kDummy) && (t != kDisabled))
@@ -399,10 +411,10 @@ __global__ void __launch_bounds__(kThreads) k_assign_pressure(uint64_t n, Partic
 
 // Computer::ModifyByPressureGradient, first loop (midpoint form), Computer.hpp:1447-1541
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_gradient(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_gradient(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	Vec<D>* __restrict__ du, EnvConst env, const DevScalars* __restrict__ sc)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	if (P.type[i] != kFluid) return;
 	const double dt = sc->dt;
@@ -429,9 +441,9 @@ __global__ void __launch_bounds__(kThreads) k_gradient(uint64_t n, Particles<D> 
 
 // second loops of ModifyByPressureGradient (Computer.hpp:1544-1563) and DynamicStabilize (Computer.hpp:1638-1655)
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_apply_du(uint64_t n, Particles<D> P, const Vec<D>* __restrict__ du, const DevScalars* __restrict__ sc)
+__global__ void __launch_bounds__(kThreads) k_apply_du(uint64_t first, uint64_t n, Particles<D> P, const Vec<D>* __restrict__ du, const DevScalars* __restrict__ sc)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	if (P.type[i] != kFluid) return;
 	const double dt = sc->dt;
@@ -445,10 +457,10 @@ __global__ void __launch_bounds__(kThreads) k_apply_du(uint64_t n, Particles<D> 
 
 // Computer::DynamicStabilize, first loop, Computer.hpp:1576-1635
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_ds(uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+__global__ void __launch_bounds__(kThreads) k_ds(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
 	const Vec<D>* __restrict__ x0, Vec<D>* __restrict__ du, EnvConst env, const DevScalars* __restrict__ sc)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	if (P.type[i] != kFluid) return;
 	const double dt = sc->dt;
@@ -611,34 +623,52 @@ inline Lists lists(mps_solver* s) { return Lists{ s->nbr_ptr.p, s->nbr.p }; }
 #define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
 #define MPS_DISPATCH(fn, ...) (s->env.dim == 2 ? fn<2>(__VA_ARGS__) : fn<3>(__VA_ARGS__))
 
+// Every stage below runs over the rows this rank owns, [own0, own1): all rows on one GPU; one x-slab of the cell-sorted
+// slots per rank when a communicator is attached (mps_comm.cu), in which case fields that neighbours read are
+// all-gathered after the stages that write them.
 template<int D> cudaError_t density(mps_solver* s, bool count_rows)
 {
+	const uint64_t r0 = s->own0(), r1 = s->own1();
 	if (s->n == 0) return cudaSuccess;
-	const unsigned nb = blocks_for(s->n, kThreads);
+	const unsigned nb = blocks_for(r1 - r0, kThreads);
 	if (count_rows)
 	{
 		MPS_TRY(s->row_len.ensure(s->n, s->stream));
-		k_density<D, true><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, s->row_len.p, reinterpret_cast<Vec<D>*>(s->x0.p), s->env);
+		if (s->comm.on)
+		{
+			// rows of other ranks have no entries here; originalX is needed for every row (DynamicStabilize reads neighbours')
+			MPS_TRY(cudaMemsetAsync(s->row_len.p, 0, s->n * sizeof(uint32_t), s->stream));
+			k_save_x<D><<<blocks_for(s->n, kThreads), kThreads, 0, s->stream>>>(s->n, view<D>(s), reinterpret_cast<Vec<D>*>(s->x0.p));
+			s->stats.kernel_launches += 1;
+		}
+		if (nb) k_density<D, true><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->row_len.p, reinterpret_cast<Vec<D>*>(s->x0.p), s->env);
 	}
-	else
-		k_density<D, false><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, nullptr, nullptr, s->env);
+	else if (nb)
+		k_density<D, false><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, nullptr, nullptr, s->env);
 	s->stats.kernel_launches += 1;
+	MPS_TRY(comm_allgather_state(s, false, false, false, true)); // N is part of the state callers read back (CSV column n)
 	return cudaGetLastError();
 }
 template<int D> cudaError_t ecs(mps_solver* s)
 {
-	if (s->n == 0) return cudaSuccess;
-	k_ecs<D><<<blocks_for(s->n, kThreads), kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, s->ecs.p, s->env);
+	const uint64_t r0 = s->own0(), r1 = s->own1();
+	if (r1 == r0) return cudaSuccess;
+	k_ecs<D><<<blocks_for(r1 - r0, kThreads), kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, s->env);
 	s->stats.kernel_launches += 1;
 	return cudaGetLastError();
 }
 template<int D> cudaError_t explicit_forces(mps_solver* s)
 {
+	const uint64_t r0 = s->own0(), r1 = s->own1();
 	if (s->n == 0) return cudaSuccess;
-	const unsigned nb = blocks_for(s->n, kThreads);
-	k_explicit_accel<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->du.p), s->env);
-	k_explicit_move<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), reinterpret_cast<Vec<D>*>(s->wall.p), s->d_sc);
-	s->stats.kernel_launches += 2;
+	const unsigned nb = blocks_for(r1 - r0, kThreads);
+	if (nb)
+	{
+		k_explicit_accel<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->du.p), s->env);
+		k_explicit_move<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), reinterpret_cast<Vec<D>*>(s->wall.p), s->d_sc);
+		s->stats.kernel_launches += 2;
+	}
+	MPS_TRY(comm_allgather_state(s, true, true, false)); // everybody needs the moved x, u
 	return cudaGetLastError();
 }
 template<int D> cudaError_t save_x(mps_solver* s)
@@ -653,22 +683,24 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 {
 	const uint64_t n = s->n;
 	if (n == 0) { s->cg.n = 0; return cudaSuccess; }
-	const unsigned nb = blocks_for(n, kThreads);
+	const uint64_t r0 = s->own0(), r1 = s->own1();
+	const unsigned nb = blocks_for(r1 - r0, kThreads);
 	cudaStream_t st = s->stream;
 	MPS_TRY(s->row_len.ensure(n, st));
 	if (recount)
 	{
-		k_row_len<D><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->row_len.p, s->env);
+		if (s->comm.on) MPS_TRY(cudaMemsetAsync(s->row_len.p, 0, n * sizeof(uint32_t), st));
+		if (nb) k_row_len<D><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->row_len.p, s->env);
 		s->stats.kernel_launches += 1;
 	}
 	CgBuffers& cg = s->cg;
 	MPS_TRY(cg.rowptr.ensure(n + 1, st));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->row_len.p, cg.rowptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
 	// the streaming kernel stages even-aligned windows: one element of slack behind every vector
-	MPS_TRY(cg.b.ensure(n + 16, st)); MPS_TRY(cg.x.ensure(n + 16, st)); if (!cg.chunked) MPS_TRY(cg.r.ensure(n + 16, st));
-	MPS_TRY(cg.ap.ensure(n + 16, st));
-	if (cg.chunked) { MPS_TRY(cg.z0.ensure(2 * (n + 16), st)); MPS_TRY(cg.z1.ensure(2 * (n + 16), st)); }
-	else { MPS_TRY(cg.p0.ensure(n + 16, st)); MPS_TRY(cg.p1.ensure(n + 16, st)); }
+	MPS_TRY(cg.b.ensure(n + 64, st)); MPS_TRY(cg.x.ensure(n + 64, st)); if (!cg.chunked) MPS_TRY(cg.r.ensure(n + 64, st));
+	MPS_TRY(cg.ap.ensure(n + 64, st));
+	if (cg.chunked) { MPS_TRY(cg.z0.ensure(2 * (n + 64), st)); MPS_TRY(cg.z1.ensure(2 * (n + 64), st)); }
+	else { MPS_TRY(cg.p0.ensure(n + 64, st)); MPS_TRY(cg.p1.ensure(n + 64, st)); }
 	cg.n = n; cg.external = false;
 	PpeOut out{};
 	if (cg.chunked)
@@ -684,37 +716,61 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 		out.row_ptr = cg.rowptr.p; out.col = cg.col.p; out.val = cg.val.p;
 	}
 	MPS_TRY(cudaMemsetAsync(&s->d_sc->active_rows, 0, sizeof(unsigned long long), st));
-	if (cg.chunked)
-		k_ppe_fill<D, true><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
-	else
-		k_ppe_fill<D, false><<<nb, kThreads, 0, st>>>(n, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
-	s->stats.kernel_launches += 1;
+	if (s->comm.on)
+	{
+		// rows of other ranks: b = 0 and the initial guess x = P (their windows are gathered like any other column)
+		k_ppe_guess<D><<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, view<D>(s), cg.b.p, cg.x.p);
+		s->stats.kernel_launches += 1;
+	}
+	if (nb)
+	{
+		if (cg.chunked)
+			k_ppe_fill<D, true><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
+		else
+			k_ppe_fill<D, false><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
+		s->stats.kernel_launches += 1;
+	}
 	MPS_TRY(cudaMemcpyAsync(&s->d_sc->nnz_total, cg.rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
 	return cudaGetLastError();
 }
 template<int D> cudaError_t assign_pressure(mps_solver* s)
 {
+	const uint64_t r0 = s->own0(), r1 = s->own1();
 	if (s->n == 0) return cudaSuccess;
-	k_assign_pressure<D><<<blocks_for(s->n, kThreads), kThreads, 0, s->stream>>>(s->n, view<D>(s), s->cg.x.p);
-	s->stats.kernel_launches += 1;
+	if (r1 > r0)
+	{
+		k_assign_pressure<D><<<blocks_for(r1 - r0, kThreads), kThreads, 0, s->stream>>>(r0, r1, view<D>(s), s->cg.x.p);
+		s->stats.kernel_launches += 1;
+	}
+	MPS_TRY(comm_allgather_state(s, false, false, true)); // the pressure gradient reads the neighbours' pressures
 	return cudaGetLastError();
 }
 template<int D> cudaError_t gradient(mps_solver* s)
 {
+	const uint64_t r0 = s->own0(), r1 = s->own1();
 	if (s->n == 0) return cudaSuccess;
-	const unsigned nb = blocks_for(s->n, kThreads);
-	k_gradient<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->du.p), s->env, s->d_sc);
-	k_apply_du<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), s->d_sc);
-	s->stats.kernel_launches += 2;
+	const unsigned nb = blocks_for(r1 - r0, kThreads);
+	if (nb)
+	{
+		k_gradient<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->du.p), s->env, s->d_sc);
+		k_apply_du<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), s->d_sc);
+		s->stats.kernel_launches += 2;
+	}
+	MPS_TRY(comm_allgather_state(s, true, true, false));
 	return cudaGetLastError();
 }
 template<int D> cudaError_t ds(mps_solver* s)
 {
+	const uint64_t r0 = s->own0(), r1 = s->own1();
 	if (s->n == 0) return cudaSuccess;
-	const unsigned nb = blocks_for(s->n, kThreads);
-	k_ds<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->x0.p), reinterpret_cast<Vec<D>*>(s->du.p), s->env, s->d_sc);
-	k_apply_du<D><<<nb, kThreads, 0, s->stream>>>(s->n, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), s->d_sc);
-	s->stats.kernel_launches += 2;
+	const unsigned nb = blocks_for(r1 - r0, kThreads);
+	if (nb)
+	{
+		k_ds<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->x0.p), reinterpret_cast<Vec<D>*>(s->du.p), s->env, s->d_sc);
+		k_apply_du<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), s->d_sc);
+		s->stats.kernel_launches += 2;
+	}
+	MPS_TRY(comm_allgather_state(s, true, true, false));
 	return cudaGetLastError();
 }
 template<int D> cudaError_t max_u2(mps_solver* s)

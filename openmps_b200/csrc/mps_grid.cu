@@ -122,11 +122,11 @@ __global__ void __launch_bounds__(kThreads) k_reorder(uint64_t n, const uint32_t
 
 // Computer.hpp:720-755.  FILL = false counts, FILL = true writes the list at nbr_ptr[i].
 template<int D, bool FILL>
-__global__ void __launch_bounds__(kThreads) k_search(uint64_t n, const Vec<D>* __restrict__ pos, const uint32_t* __restrict__ skey,
+__global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n, const Vec<D>* __restrict__ pos, const uint32_t* __restrict__ skey,
 	const uint64_t* __restrict__ cell_start, uint32_t* __restrict__ nbr_cnt, const uint64_t* __restrict__ nbr_ptr,
 	uint32_t* __restrict__ nbr, EnvConst env)
 {
-	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t k = skey[i];
 	if (k == static_cast<uint32_t>(env.ncells))
@@ -257,8 +257,12 @@ cudaError_t sort_and_search(mps_solver* s)
 	s->stats.kernel_launches += 4;
 
 	// 4. neighbour list: count -> row pointers -> fill
+	// lists are built for the rows this rank owns (all of them on one GPU)
 	const Vec<D>* pos = next.pos;
-	k_search<D, false><<<nb, kThreads, 0, st>>>(n, pos, s->skey.p, s->cell_start.p, s->nbr_cnt.p, nullptr, nullptr, env);
+	const uint64_t r0 = s->own0(), r1 = s->own1();
+	const unsigned nbo = blocks_for(r1 - r0, kThreads);
+	if (s->comm.on) MPS_TRY(cudaMemsetAsync(s->nbr_cnt.p, 0, n * sizeof(uint32_t), st));
+	if (nbo) k_search<D, false><<<nbo, kThreads, 0, st>>>(r0, r1, pos, s->skey.p, s->cell_start.p, s->nbr_cnt.p, nullptr, nullptr, env);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->nbr_cnt.p, s->nbr_ptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
 	// the list length is needed on the host to size the buffer: one 8-byte read-back per step
@@ -266,7 +270,7 @@ cudaError_t sort_and_search(mps_solver* s)
 	MPS_TRY(cudaMemcpyAsync(&total, s->nbr_ptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 	MPS_TRY(cudaStreamSynchronize(st));
 	MPS_TRY(s->nbr.ensure(total + 1, st));
-	k_search<D, true><<<nb, kThreads, 0, st>>>(n, pos, s->skey.p, s->cell_start.p, nullptr, s->nbr_ptr.p, s->nbr.p, env);
+	if (nbo) k_search<D, true><<<nbo, kThreads, 0, st>>>(r0, r1, pos, s->skey.p, s->cell_start.p, nullptr, s->nbr_ptr.p, s->nbr.p, env);
 	s->stats.kernel_launches += 1;
 	s->nbr_total = total;
 	s->searched = true;

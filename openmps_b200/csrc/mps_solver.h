@@ -71,10 +71,23 @@ struct CgBuffers
 	DevBuf<ChunkDesc> desc;
 	DevBuf<unsigned char> blobs;
 	uint64_t desc_cap = 0;
+	DevBuf<CgStepScalars> step;      // multi-GPU stepwise solve: scalars of the recurrence on the device ...
+	CgStepScalars* h_step = nullptr; // ... and their pinned host mirror (convergence test)
 	DevBuf<unsigned long long> prof; // per-CTA cycle counters of the last streaming solve (mps_get_cg_profile)
 	unsigned prof_blocks = 0;
 };
 
+} // namespace mps
+
+namespace mps {
+// one rank of a multi-GPU run (mps_comm.cu): NCCL communicator + this rank's slab of the cell-sorted slots
+struct Comm
+{
+	bool on = false;
+	int rank = 0, nranks = 1;
+	void* nccl = nullptr;     // ncclComm_t
+	DevBuf<unsigned long long> ext;  // halo extents of all ranks (2 per rank), device
+};
 } // namespace mps
 
 struct mps_solver
@@ -84,6 +97,7 @@ struct mps_solver
 	cudaStream_t stream = nullptr;
 	mps::EnvConst env{};
 	std::string last_error;
+	std::string comm_error;  // text of the last NCCL failure (reported through last_error)
 
 	uint64_t n = 0;          // particles (all types, including Disabled)
 	int cur = 0;             // which of the two state copies is live
@@ -136,6 +150,12 @@ struct mps_solver
 	bool cg_profile = false;
 
 	int vec_stride() const { return env.dim == 2 ? 2 : 4; }
+
+	// multi-GPU: rows (slots) this rank computes; the state itself is replicated (DESIGN.md "multi-GPU")
+	mps::Comm comm;
+	uint64_t slab() const { return comm.on ? (n + comm.nranks - 1) / comm.nranks : n; }
+	uint64_t own0() const { const uint64_t b = static_cast<uint64_t>(comm.rank) * slab(); return comm.on ? (b < n ? b : n) : 0; }
+	uint64_t own1() const { const uint64_t e = static_cast<uint64_t>(comm.rank + 1) * slab(); return comm.on ? (e < n ? e : n) : n; }
 };
 
 namespace mps {
@@ -162,6 +182,9 @@ cudaError_t launch_scatter_from_orig(mps_solver* s, const double* d_x, const dou
 cudaError_t launch_gather_to_orig(mps_solver* s, double* d_x, double* d_u, double* d_p, double* d_n, int32_t* d_type);
 cudaError_t launch_set_wall(mps_solver* s, uint64_t count, const uint64_t* d_ids, const double* d_x);
 cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
+// mps_comm.cu
+cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden = false); // no-op without a communicator
+cudaError_t comm_cg_solve(mps_solver* s);                                       // multi-rank CG (stepwise kernels + NCCL)
 // mps_scan.cu
 cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /* n + 1 */, uint64_t n, DevBuf<uint64_t>& tmp, cudaStream_t st,
 	uint64_t* launches);
@@ -170,6 +193,9 @@ cudaError_t launch_chunk_build(mps_solver* s);          // row_len, skey, cell_s
 // mps_cg.cu
 cudaError_t cg_configure(mps_solver* s);                // picks chunk limits / pipeline depth for this environment
 cudaError_t launch_cg(mps_solver* s);
+cudaError_t launch_cg_step(mps_solver* s, int phase, CgStepScalars* st);    // one phase of the streaming CG as its own launch
+cudaError_t launch_cg_reduce(mps_solver* s, double* dst);                   // per-CTA partials -> *dst, fixed order
+cudaError_t launch_cg_scalars(mps_solver* s, int which, CgStepScalars* st); // 0 after r0, 1 after an iteration, 2 finish
 cudaError_t cg_time_iteration(mps_solver* s, int reps, double* mean_ms, double* bytes);
 
 inline unsigned int blocks_for(uint64_t n, unsigned int threads) { return static_cast<unsigned int>((n + threads - 1) / threads); }

@@ -1,0 +1,92 @@
+"""Multi-GPU slab decomposition.  CPU part: the partition arithmetic and the launcher-side plumbing on a
+2-rank gloo group.  GPU part (needs >= 2 GPUs): 2-GPU run == 1-GPU run on the same input."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openmps_b200 import capi  # noqa: E402
+
+
+@pytest.mark.parametrize("n,nranks", [(0, 1), (1, 4), (10, 3), (1008104, 8), (123147, 2), (7, 8)])
+def test_partition_tiles_the_slots(n, nranks):
+    ranges = [capi.partition_range(n, nranks, r) for r in range(nranks)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    for (a, b), (c, d) in zip(ranges, ranges[1:]):
+        assert a <= b == c <= d
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) == (n + nranks - 1) // nranks if n else max(sizes) == 0
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from openmps_b200 import capi
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 1008104
+# launcher plumbing: a 128-byte id made on rank 0 reaches every rank unchanged
+uid = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    uid = torch.arange(128, dtype=torch.uint8)
+dist.broadcast(uid, 0)
+assert bytes(uid.numpy().tobytes()) == bytes(range(128))
+# every rank derives the same decomposition; together the slabs tile the slots exactly once
+mine = torch.tensor(capi.partition_range(n, world, rank), dtype=torch.int64)
+alls = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(alls, mine)
+cover = torch.zeros(n, dtype=torch.int32)
+for a, b in (t.tolist() for t in alls):
+    cover[a:b] += 1
+assert int(cover.min()) == 1 and int(cover.max()) == 1
+# the weak-scaling reduction bench.py uses: max over ranks of the per-rank time
+t = torch.tensor([1.0 + rank], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert float(t) == float(world)
+dist.destroy_process_group()
+print("GLOO_OK", rank)
+"""
+
+
+def test_two_rank_gloo_partition_and_plumbing(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("GLOO_OK") == 2
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,steps", [("dambreak2d", 5), ("static", 3), ("dambreak3d", 2)])
+def test_two_gpus_match_one_gpu(scene, steps):
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29612", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), scene, str(steps)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    rows = [json.loads(l[5:]) for l in r.stdout.splitlines() if l.startswith("MGPU ")]
+    assert len(rows) == 2
+    r0 = next(x for x in rows if x["rank"] == 0)
+    assert all(x["replicas_equal"] for x in rows)
+    assert r0["type_equal"]
+    # only the summation order of the CG dot products differs between 1 and 2 GPUs
+    assert r0["err_x"] <= 1e-9 and r0["err_u"] <= 1e-6 and r0["err_n"] <= 1e-9 and r0["err_p"] <= 1e-5, r0
+    assert abs(r0["iters"] - r0["iters_1gpu"]) <= max(3, 0.01 * r0["iters_1gpu"]), r0
+    assert r0["comm_calls"] and r0["comm_calls"] > 0

@@ -145,10 +145,15 @@ int mps_get_solution(mps_handle h, uint64_t n, double* x);
  * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,
  * a file ...), every rank attaches it to its handle BEFORE the first step and then adds the SAME particles in the same
  * order.  The particle state is replicated; each rank computes the x-slab [own_first, own_last) of the cell-sorted slots
- * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu. */
+ * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu.  NCCL carries the per-stage field
+ * all-gathers; the CG iteration itself runs over peer memory (mps_comm_mode). */
 int mps_comm_unique_id(void* out128);
 int mps_comm_init(mps_handle h, int rank, int nranks, const void* id128);
 int mps_comm_info(mps_handle h, int* rank, int* nranks, uint64_t* own_first, uint64_t* own_last);
+/* how the ranks' CG solves are coupled: 0 not decided yet (before the first assembly) / single GPU, 1 peer memory over NVLink
+ * (ONE persistent kernel per solve on every rank; rim rows and dot products cross GPUs by P2P stores, mps_cg.cu), 2 NCCL between
+ * per-phase launches (chosen when the ranks cannot map each other's memory, or with MPS_COMM_NCCL_ONLY=1) */
+int mps_comm_mode(mps_handle h, int* mode);
 /* the slab arithmetic on its own (host only, needs no GPU): slots [first, last) of `rank` among `nranks` for n particles */
 int mps_partition_range(uint64_t n, int nranks, int rank, uint64_t* first, uint64_t* last);
 

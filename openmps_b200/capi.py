@@ -104,6 +104,7 @@ def load_library():
     sig("mps_comm_unique_id", [vp])
     sig("mps_comm_init", [vp, C.c_int, C.c_int, vp])
     sig("mps_comm_info", [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64)])
+    sig("mps_comm_mode", [vp, C.POINTER(C.c_int)])
     sig("mps_partition_range", [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)])
     sig("mps_set_cg_profile", [vp, C.c_int])
     sig("mps_get_cg_profile", [vp, pd])
@@ -229,6 +230,9 @@ class GpuComputer:
         self._check(self.lib.mps_determine_dt(self.h, C.byref(dt)))
         return dt.value
 
+    def set_time(self, t, dt):
+        self._check(self.lib.mps_set_time(self.h, float(t), float(dt)))
+
     def time(self):
         t, dt = C.c_double(), C.c_double()
         self._check(self.lib.mps_get_time(self.h, C.byref(t), C.byref(dt)))
@@ -353,7 +357,9 @@ class GpuComputer:
     def comm_info(self):
         r, n, a, b = C.c_int(), C.c_int(), C.c_uint64(), C.c_uint64()
         self._check(self.lib.mps_comm_info(self.h, C.byref(r), C.byref(n), C.byref(a), C.byref(b)))
-        return {"rank": r.value, "nranks": n.value, "own": (a.value, b.value)}
+        m = C.c_int()
+        self._check(self.lib.mps_comm_mode(self.h, C.byref(m)))
+        return {"rank": r.value, "nranks": n.value, "own": (a.value, b.value), "mode": {0: "single", 1: "peer-memory", 2: "nccl"}[m.value]}
 
     def set_cg_profile(self, on):
         self._check(self.lib.mps_set_cg_profile(self.h, 1 if on else 0))

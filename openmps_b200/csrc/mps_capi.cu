@@ -255,6 +255,7 @@ int mps_destroy(mps_handle s)
 	NEED(s);
 	cudaSetDevice(s->device);
 	cudaStreamSynchronize(s->stream);
+	comm_release_peers(s); // un-maps the peers' arenas, frees ours (cg.z0 / z1 point into it)
 	mps_comm_release(s);
 	s->comm.ext.release(); s->cg.step.release();
 	if (s->cg.h_step) cudaFreeHost(s->cg.h_step);

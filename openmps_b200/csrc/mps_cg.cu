@@ -217,6 +217,7 @@ struct CgStreamArgs
 	uint64_t n;
 	const ChunkDesc* desc;
 	const unsigned char* blobs;
+	const uint32_t* chunk_of_row; // row -> chunk (bounds the chunks of the rows this rank owns)
 	const double* b;
 	double* x;
 	double2* z0;               // {r_i, p_i} interleaved, ping-pong pair: ONE window copy per range brings both gathered vectors
@@ -231,6 +232,7 @@ struct CgStreamArgs
 	int l2_stream;             // blobs do not fit L2: stream them evict_first
 	unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (mps_get_cg_profile), nullptr = off
 	uint64_t own0, own1;       // rows this rank updates ([0, n) on one GPU)
+	PeerLink peer;             // multi-GPU persistent solve (k_cg_stream<LPR, true>): neighbours' buffers and mailboxes over NVLink
 };
 
 constexpr int kMaxStreamWarps = 17;
@@ -283,6 +285,118 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 	__syncthreads();
 }
 
+// ---- multi-GPU: the same persistent kernel on every rank, coupled through peer memory over NVLink (no NCCL and no host in
+//      the iteration).  Two things cross GPUs:
+//   * the rim of {r, p}: the part of a chunk's window that lies in a neighbour rank's slab is fetched by the producer warp
+//     straight from that rank's buffer (the same bulk async copy, peer address as its source: the transfer rides the ring
+//     of stages like any other window copy, NVLink latency hidden by the look-ahead); nobody keeps copies of foreign rows;
+//   * the two dot products per iteration: CTA 0 of every rank sums its grid's partials and stores {sum, sequence flag} into
+//     the mailbox of every rank, its own included (value first, flag with release.sys); every CTA of every rank waits for
+//     the flags of all ranks in its own rank's mailbox and adds the values in rank order (the same order everywhere: every
+//     CTA of every rank gets the same bits and takes the same convergence decision).
+//   The exchange doubles as the grid barrier and as the cross-GPU barrier that orders the rim reads after the owner's writes
+//   (a thread that writes a row a neighbour reads fences at system scope before its CTA arrives).
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v)
+{
+	asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// A peer that never arrives (a rank that died) must end as a trapped launch, never as a hung GPU: waits are bounded in time.
+constexpr unsigned long long kPeerWaitNs = 30ull * 1000ull * 1000ull * 1000ull;
+
+// is `row` (one of this rank's) inside a neighbour rank's windows?  Its {r, p} is then read by that rank over NVLink, so the
+// thread that wrote it fences at system scope before its CTA arrives at the next reduction
+__device__ __forceinline__ bool exposed_row(const PeerLink& pl, const uint64_t row)
+{
+	return (row >= pl.exp_b[0] && row < pl.exp_e[0]) || (row >= pl.exp_b[1] && row < pl.exp_e[1]);
+}
+
+// Sum of `local` over every thread of every CTA of every rank; `seq` counts the reductions of this solve.  One GPU: per-CTA
+// partials, grid barrier, every CTA adds the partials in the same fixed order.  Multi-GPU: see above.
+template<bool MG>
+__device__ __forceinline__ double all_sum(const CgStreamArgs& a, double local, double* part, double* red, unsigned long long& bar_target,
+	unsigned long long& seq, const unsigned nblocks)
+{
+	local = block_sum_n(local, red);
+	if (!MG)
+	{
+		if (threadIdx.x == 0) part[blockIdx.x] = local;
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		return grid_sum_n(part, nblocks, red);
+	}
+	const PeerLink& pl = a.peer;
+	seq++;
+	const unsigned long long want = pl.tag | seq;
+	const unsigned slot = static_cast<unsigned>(seq & 3ull);
+	if (threadIdx.x < 32)
+	{
+		const unsigned lane = threadIdx.x;
+		if (blockIdx.x != 0)
+		{
+			if (lane == 0)
+			{
+				part[blockIdx.x] = local;
+				async::red_release_gpu_add(&a.sc->grid_barrier, 1ull);
+			}
+		}
+		else
+		{
+			// CTA 0: wait for the other CTAs of this grid, add the partials in a fixed order, send the sum to every rank
+			bar_target += nblocks - 1;
+			if (lane == 0)
+			{
+				part[0] = local;
+				for (unsigned spin = 0; async::ld_acquire_gpu(&a.sc->grid_barrier) < bar_target; spin++)
+					if (spin > (1u << 27)) __trap();
+			}
+			__syncwarp();
+			double v = 0.0;
+			for (unsigned k = lane; k < nblocks; k += 32) v += __ldcg(part + k);
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			if (lane < static_cast<unsigned>(pl.nranks))
+			{
+				// my sum into everybody's mailbox (my own included): value, then the flag with release semantics at system scope
+				PeerMail* out = pl.mail[lane] + slot * kMaxPeerRanks + pl.rank;
+				st_relaxed_sys_f64(&out->value, v);
+				st_release_sys(&out->flag, want);
+			}
+		}
+		// every CTA: the sums of all ranks arrive in this rank's mailbox; add them in rank order (identical bits on every rank)
+		double mine = 0.0;
+		if (lane < static_cast<unsigned>(pl.nranks))
+		{
+			const PeerMail* in = pl.mail[pl.rank] + slot * kMaxPeerRanks + lane;
+			const unsigned long long t0 = globaltimer_ns();
+			for (unsigned spin = 0; ld_acquire_sys(&in->flag) != want; spin++)
+				if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > kPeerWaitNs) __trap();
+			mine = __ldcg(&in->value);
+		}
+		double total = 0.0;
+		for (int r = 0; r < pl.nranks; r++) total += __shfl_sync(0xffffffffu, mine, r);
+		if (lane == 0) red[0] = total;
+	}
+	__syncthreads();
+	const double total = red[0];
+	__syncthreads(); // red is reused by the next block_sum_n
+	return total;
+}
+
 struct StreamSmem
 {
 	unsigned char* base;
@@ -303,7 +417,7 @@ struct StreamSmem
 // One SpMV phase over this CTA's chunks.  ITER = false: r = b - A x, p_prev = 0 (window of x; result into zcur).
 // ITER = true: p = r + beta p_prev, Ap = A p (window of zprev = {r, p_prev}; p into zcur[].y).
 // Returns this thread's share of r.r / p.Ap.  `it` counts the ring uses so far.
-template<int LPR, bool ITER>
+template<int LPR, bool ITER, bool MG>
 __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const StreamSmem& sm, const uint32_t c0, const uint32_t c1, const uint32_t live,
 	uint32_t& it, uint32_t& dseq, const double beta, const double2* __restrict__ zprev, double2* __restrict__ zcur,
 	const uint64_t pol_matrix, const uint64_t pol_vector)
@@ -370,7 +484,21 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 					async::mbar_arrive_expect_tx(&sm.full[s], d->blob_bytes + d->window * (ITER ? 16u : 8u));
 				}
 				__syncwarp();
-				if (bytes) async::bulk_g2s(dst, src, bytes, &sm.full[s], lane == 0 ? pol_matrix : pol_vector);
+				if (MG && ITER && lane != 0 && bytes)
+				{
+					// multi-GPU: slots below own0 / from own1 on live in the left / right neighbour's buffer (same index, its memory)
+					const PeerLink& pl = a.peer;
+					const double2* nbz[2] = { (zprev == a.z0) ? pl.nb_z0[0] : pl.nb_z1[0], (zprev == a.z0) ? pl.nb_z0[1] : pl.nb_z1[1] };
+					const uint64_t lo = nbz[0] ? a.own0 : 0ull, hi = nbz[1] ? a.own1 : ~0ull;
+					const uint64_t rb = d->range_start[lane - 1], re = rb + d->range_len[lane - 1];
+					double2* wdst = static_cast<double2*>(dst);
+					const uint64_t m0 = rb < lo ? (re < lo ? re : lo) : rb; // [rb, m0) left neighbour
+					const uint64_t m1 = re > hi ? (rb > hi ? rb : hi) : re; // [m1, re) right neighbour
+					if (m0 > rb) async::bulk_g2s(wdst, nbz[0] + rb, static_cast<uint32_t>(m0 - rb) * 16u, &sm.full[s], pol_vector);
+					if (m1 > m0) async::bulk_g2s(wdst + (m0 - rb), zprev + m0, static_cast<uint32_t>(m1 - m0) * 16u, &sm.full[s], pol_vector);
+					if (re > m1) async::bulk_g2s(wdst + (m1 - rb), nbz[1] + m1, static_cast<uint32_t>(re - m1) * 16u, &sm.full[s], pol_vector);
+				}
+				else if (bytes) async::bulk_g2s(dst, src, bytes, &sm.full[s], lane == 0 ? pol_matrix : pol_vector);
 			}
 			__syncwarp(); // every lane is done reading this half
 			if (lane == 0 && bidx + 2 < nbatch) fetch_batch(bidx + 2, seq + 2);
@@ -386,6 +514,7 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 		const unsigned group = warp / gwarps;
 		const unsigned ctid = threadIdx.x - group * gwarps * 32, nct = gwarps * 32;
 		const uint32_t lr = ctid / LPR, sl = ctid % LPR;
+		bool pushed = false;
 		for (uint32_t q = group; q < live; q += kGroups)
 		{
 			const uint32_t k = it + q;
@@ -453,12 +582,14 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 				{
 					const double ri = a.b[row] - acc;
 					zcur[row] = make_double2(ri, 0.0);
+					if (MG) pushed |= exposed_row(a.peer, row);
 					local = fma(ri, ri, local);
 				}
 			}
 			__syncwarp();
 			if (lane == 0) async::mbar_arrive(&sm.empty[s]); // this warp is done reading stage s
 		}
+		if (MG && pushed) __threadfence_system(); // rim rows are visible at system scope before this CTA's arrival is seen
 	}
 	it += live;
 	return local;
@@ -476,7 +607,7 @@ struct StreamCta
 	uint64_t pol_matrix, pol_vector;
 };
 
-template<bool ZERO_ROWS>
+template<bool ZERO_ROWS, bool MG = false>
 __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigned char* smem_raw)
 {
 	const uint32_t S = a.stages;
@@ -504,11 +635,14 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 		async::mbar_init_fence();
 		// this CTA's run of chunks: split the modelled cost evenly (descriptors hold its exclusive prefix)
 		const uint64_t nchunks = a.sc->n_chunks, total = a.sc->cost_total;
+		// multi-GPU: only the chunks that hold rows of this rank (all others are empty here and would only be walked over)
+		const uint64_t chunk_lo = (a.own1 > a.own0) ? a.chunk_of_row[a.own0] : 0;
+		const uint64_t chunk_hi = (a.own1 > a.own0) ? a.chunk_of_row[a.own1 - 1] + 1ull : 0;
 		uint32_t bound[2];
 		for (int w = 0; w < 2; w++)
 		{
 			const uint64_t b = blockIdx.x + w;
-			if (b >= nblocks) { bound[w] = static_cast<uint32_t>(nchunks); continue; }
+			if (b >= nblocks) { bound[w] = static_cast<uint32_t>(chunk_hi); continue; }
 			const uint64_t target = total / nblocks * b + (total % nblocks) * b / nblocks;
 			uint64_t lo = 0, hi = nchunks; // first chunk with cost_off >= target
 			while (lo < hi)
@@ -516,7 +650,7 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 				const uint64_t mid = (lo + hi) >> 1;
 				if (a.desc[mid].cost_off < target) lo = mid + 1; else hi = mid;
 			}
-			bound[w] = static_cast<uint32_t>(lo);
+			bound[w] = static_cast<uint32_t>(lo < chunk_lo ? chunk_lo : (lo > chunk_hi ? chunk_hi : lo));
 		}
 		ctl[0] = bound[0]; ctl[1] = bound[1]; ctl[2] = 0;
 		uint64_t r0 = (bound[0] < nchunks) ? a.desc[bound[0]].row_begin : n;
@@ -535,7 +669,15 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 		for (uint32_t k = c.c0 + threadIdx.x; k < c.c1; k += nthreads) mine += (a.desc[k].nnz != 0) ? 1u : 0u;
 		if (mine) atomicAdd(&ctl[2], mine);
 		if (ZERO_ROWS)
-			for (uint64_t i = c.row0 + threadIdx.x; i < c.row1; i += nthreads) { a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0; }
+		{
+			bool pushed = false;
+			for (uint64_t i = c.row0 + threadIdx.x; i < c.row1; i += nthreads)
+			{
+				a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0;
+				if (MG) pushed |= exposed_row(a.peer, i);
+			}
+			if (MG && pushed) __threadfence_system();
+		}
 	}
 	__syncthreads();
 	c.live = ctl[2];
@@ -545,11 +687,13 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 }
 
 // phase 2 over rows [row0, row1): x += alpha p ; r -= alpha Ap ; returns this thread's share of r.r (4 independent rows in flight)
+template<bool MG = false>
 __device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint64_t row0, const uint64_t row1, const double alpha,
 	const double2* __restrict__ zprev, double2* __restrict__ zcur)
 {
 	const unsigned nthreads = blockDim.x;
 	double local = 0.0;
+	bool pushed = false;
 	for (uint64_t base = row0 + threadIdx.x; base < row1; base += 4ull * nthreads)
 	{
 		double pv[4], xv[4], av[4], rv[4];
@@ -569,18 +713,20 @@ __device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint6
 				a.x[i] = fma(alpha, pv[q], xv[q]);
 				const double ri = fma(-alpha, av[q], rv[q]);
 				zcur[i].x = ri;
+				if (MG) pushed |= exposed_row(a.peer, i); // the finished {r', p} of a rim row
 				local = fma(ri, ri, local);
 			}
 		}
 	}
+	if (MG && pushed) __threadfence_system();
 	return local;
 }
 
-template<int LPR>
+template<int LPR, bool MG>
 __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const StreamCta cta = stream_setup<true>(a, smem_raw);
+	const StreamCta cta = stream_setup<true, MG>(a, smem_raw);
 	const StreamSmem& sm = cta.sm;
 	double* red = cta.red;
 	const uint32_t c0 = cta.c0, c1 = cta.c1, live = cta.live;
@@ -590,16 +736,13 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	const unsigned nblocks = gridDim.x;
 	double* part0 = a.partials;
 	double* part1 = a.partials + nblocks;
-	unsigned long long bar_target = 0;
+	unsigned long long bar_target = 0, seq = 0;
 	uint32_t it = 0, dseq = 0;
 	const bool prof_on = (a.prof != nullptr) && (threadIdx.x == 0);
 
 	// ---- r0 = b - A x ; p_prev = 0 ; rr = r0.r0 (Computer.hpp:1382-1386) ----
-	double local = spmv_phase<LPR, false>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
-	local = block_sum_n(local, red);
-	if (threadIdx.x == 0) part0[blockIdx.x] = local;
-	grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-	double rr = grid_sum_n(part0, nblocks, red);
+	double local = spmv_phase<LPR, false, MG>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
+	double rr = all_sum<MG>(a, local, part0, red, bar_target, seq, nblocks);
 	const double rr0 = rr;
 	const double tol = rr * a.eps * a.eps;     // Computer.hpp:1386
 	bool converged = (tol == 0);                // Computer.hpp:1389
@@ -612,29 +755,23 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	{
 		// ---- phase 1: p = r + beta p_prev ; Ap = A p ; p.Ap ----
 		const long long t0 = prof_on ? clock64() : 0;
-		local = spmv_phase<LPR, true>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
-		local = block_sum_n(local, red);
-		if (threadIdx.x == 0) part1[blockIdx.x] = local;
+		local = spmv_phase<LPR, true, MG>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
 		const long long t1 = prof_on ? clock64() : 0;
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		const double pAp = all_sum<MG>(a, local, part1, red, bar_target, seq, nblocks);
 		const long long t2 = prof_on ? clock64() : 0;
-		const double pAp = grid_sum_n(part1, nblocks, red);
 		const double alpha = rr / pAp;
 
 		// ---- phase 2 over this CTA's own rows: x += alpha p ; r -= alpha Ap ; r.r ----
-		local = update_rows(a, row0, row1, alpha, zprev, zcur);
-		local = block_sum_n(local, red);
-		if (threadIdx.x == 0) part0[blockIdx.x] = local;
+		local = update_rows<MG>(a, row0, row1, alpha, zprev, zcur);
 		const long long t3 = prof_on ? clock64() : 0;
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-		const double rr_new = grid_sum_n(part0, nblocks, red);
+		const double rr_new = all_sum<MG>(a, local, part0, red, bar_target, seq, nblocks);
 		if (prof_on)
 		{
 			const long long t4 = clock64();
 			unsigned long long* pr = a.prof + blockIdx.x * 8;
-			pr[0] += static_cast<unsigned long long>(t1 - t0);  // phase 1 (SpMV + block reduction)
-			pr[2] += static_cast<unsigned long long>(t3 - t2);  // phase 2 (+ grid sum of p.Ap)
-			pr[3] += static_cast<unsigned long long>((t2 - t1) + (t4 - t3)); // both grid barriers (+ grid sum of r.r)
+			pr[0] += static_cast<unsigned long long>(t1 - t0);  // phase 1 (SpMV)
+			pr[2] += static_cast<unsigned long long>(t3 - t2);  // phase 2
+			pr[3] += static_cast<unsigned long long>((t2 - t1) + (t4 - t3)); // both reductions (block sums, grid / peer barrier, sum)
 			pr[6] += static_cast<unsigned long long>(t4 - t0);
 		}
 		iter++;
@@ -669,8 +806,8 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_step(CgStreamArg
 	double2* zprev = st->zcur_is_1 ? a.z0 : a.z1;
 	double2* zcur = st->zcur_is_1 ? a.z1 : a.z0;
 	double local = 0.0;
-	if (PHASE == 0) local = spmv_phase<LPR, false>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, 0.0, nullptr, a.z0, cta.pol_matrix, cta.pol_vector);
-	if (PHASE == 1) local = spmv_phase<LPR, true>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, st->beta, zprev, zcur, cta.pol_matrix, cta.pol_vector);
+	if (PHASE == 0) local = spmv_phase<LPR, false, false>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, 0.0, nullptr, a.z0, cta.pol_matrix, cta.pol_vector);
+	if (PHASE == 1) local = spmv_phase<LPR, true, false>(a, cta.sm, cta.c0, cta.c1, cta.live, it, dseq, st->beta, zprev, zcur, cta.pol_matrix, cta.pol_vector);
 	if (PHASE == 2) local = update_rows(a, cta.row0, cta.row1, st->rr / st->pAp, zprev, zcur);
 	local = block_sum_n(local, cta.red);
 	if (threadIdx.x == 0) a.partials[blockIdx.x] = local;
@@ -750,27 +887,34 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 	cudaError_t e = c.partials.ensure(2ull * L.grid + 8, s->stream);
 	if (e != cudaSuccess) return e;
 	CgStreamArgs& a = L.a;
-	a.n = c.n; a.desc = c.desc.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
+	a.n = c.n; a.desc = c.desc.p; a.blobs = c.blobs.p; a.chunk_of_row = c.chunk_of_row.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
 	a.ap = c.ap.p; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
 	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
 	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
 	a.l2_stream = ((s->nbr_total + (s->own1() - s->own0())) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
 	a.prof = nullptr;
 	a.own0 = s->own0(); a.own1 = s->own1();
+	a.peer = PeerLink{};
 	return cudaSuccess;
 }
 
-template<int LPR>
+template<int LPR, bool MG>
 cudaError_t launch_stream(mps_solver* s)
 {
 	CgBuffers& c = s->cg;
 	StreamLaunch L;
 	cudaError_t e = prepare_stream(s, L);
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(k_cg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	if (MG)
+	{
+		e = comm_prepare_link(s); // halo extents of this assembly -> rows to push, neighbours' buffers, mailboxes
+		if (e != cudaSuccess) return e;
+		L.a.peer = s->comm.link;
+	}
+	e = cudaFuncSetAttribute(k_cg_stream<LPR, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_stream<LPR>, L.threads, L.smem_bytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_stream<LPR, MG>, L.threads, L.smem_bytes);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
 	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
@@ -786,7 +930,19 @@ cudaError_t launch_stream(mps_solver* s)
 	}
 	void* params[] = { &L.a };
 	s->stats.kernel_launches += 1;
-	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR, MG>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+}
+
+template<bool MG>
+cudaError_t launch_stream_lpr(mps_solver* s)
+{
+	switch (s->cg.lanes_per_row)
+	{
+	case 1: return launch_stream<1, MG>(s);
+	case 2: return launch_stream<2, MG>(s);
+	case 4: return launch_stream<4, MG>(s);
+	default: return launch_stream<8, MG>(s);
+	}
 }
 
 template<int LPR, int PHASE>
@@ -841,17 +997,9 @@ cudaError_t launch_cg(mps_solver* s)
 		// an empty system is converged by definition (residual0 == 0)
 		return cudaSuccess;
 	}
-	if (c.chunked && !c.external && s->comm.on) return comm_cg_solve(s);
-	if (c.chunked && !c.external)
-	{
-		switch (c.lanes_per_row)
-		{
-		case 1: return launch_stream<1>(s);
-		case 2: return launch_stream<2>(s);
-		case 4: return launch_stream<4>(s);
-		default: return launch_stream<8>(s);
-		}
-	}
+	// multi-GPU: the persistent kernel coupled through peer memory when the ranks could map each other's arenas, else NCCL stepwise
+	if (c.chunked && !c.external && s->comm.on) return (s->comm.peer_mode == 1) ? launch_stream_lpr<true>(s) : comm_cg_solve(s);
+	if (c.chunked && !c.external) return launch_stream_lpr<false>(s);
 	CgArgs args;
 	args.n = c.n; args.rowptr = c.rowptr.p; args.col = c.col.p; args.val = c.val.p; args.b = c.b.p;
 	args.x = c.x.p; args.r = c.r.p; args.pbuf0 = c.p0.p; args.pbuf1 = c.p1.p; args.ap = c.ap.p;

@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -98,6 +99,34 @@ inline Slab slab_of(const mps_solver* s, int rank)
 	return Slab{ b, e };
 }
 
+// Halo extents of every rank (once per solve: the chunks were rebuilt by this step's assembly): ext[2k], ext[2k+1] = first /
+// one-past-last slot the windows of rank k reach.  One small all-gather + one host read-back.
+cudaError_t halo_extents(mps_solver* s, std::vector<unsigned long long>& ext)
+{
+	CgBuffers& c = s->cg;
+	cudaStream_t st = s->stream;
+	const int R = s->comm.nranks;
+	MPS_TRY(s->comm.ext.ensure(2ull * R + 2, st));
+	unsigned long long* ext_local = s->comm.ext.p + 2ull * R;
+	const unsigned long long init[2] = { s->own0(), s->own1() };
+	MPS_TRY(cudaMemcpyAsync(ext_local, init, sizeof(init), cudaMemcpyHostToDevice, st));
+	k_halo_extent<<<64, 256, 0, st>>>(c.desc.p, s->d_sc, ext_local);
+	s->stats.kernel_launches += 1;
+	MPS_NCCL(s, g_nccl.AllGather(ext_local, s->comm.ext.p, 2, ncclUint64, comm_of(s), st));
+	s->stats.comm_calls += 1;
+	ext.assign(2ull * R, 0);
+	MPS_TRY(cudaMemcpyAsync(ext.data(), s->comm.ext.p, 2ull * R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	MPS_TRY(cudaStreamSynchronize(st));
+	for (int k = 0; k < R; k++)
+	{
+		// a window must not reach past the adjacent slab (slabs thinner than one cell column are not supported)
+		const uint64_t lo_ok = (k > 0) ? static_cast<uint64_t>(k - 1) * s->slab() : 0;
+		const uint64_t hi_ok = (k + 1 < R) ? std::min<uint64_t>(static_cast<uint64_t>(k + 2) * s->slab(), s->n) : s->n;
+		if (ext[2 * k] < lo_ok || ext[2 * k + 1] > hi_ok + 1 /* window ends are rounded up to even */) { s->comm_error = "slab thinner than the neighbour stencil: use fewer GPUs for this problem"; return cudaErrorUnknown; }
+	}
+	return cudaSuccess;
+}
+
 // rim exchange of one {r, p} buffer with the two adjacent ranks (host copies of all extents in `ext`)
 cudaError_t halo_exchange(mps_solver* s, double* z, const std::vector<unsigned long long>& ext)
 {
@@ -142,35 +171,181 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 	return cudaSuccess;
 }
 
+// ---- peer-memory coupling of the persistent CG kernel ----------------------------------------------------------------------
+namespace {
+
+inline size_t arena_size(uint64_t rows) { return kPeerHeaderBytes + 2ull * rows * sizeof(double2); }
+
+struct PeerExport
+{
+	cudaIpcMemHandle_t handle; // of the allocation that contains the arena
+	unsigned long long offset; // arena base - allocation base (cudaMalloc may sub-allocate small requests)
+	unsigned long long bytes;
+	unsigned long long ok;     // 0: this rank could not export
+};
+
+// offset of `p` inside its allocation (the IPC handle always opens the allocation's base)
+bool allocation_offset(void* p, unsigned long long* offset)
+{
+	typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+	static GetRange fn = nullptr;
+	if (!fn)
+	{
+		void* sym = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return false;
+		fn = reinterpret_cast<GetRange>(sym);
+	}
+	unsigned long long base = 0; size_t size = 0;
+	if (fn(&base, &size, reinterpret_cast<unsigned long long>(p)) != 0) return false;
+	*offset = reinterpret_cast<unsigned long long>(p) - base;
+	return true;
+}
+
+// every rank's stream reaches this point before anybody continues (used before exported memory is freed)
+cudaError_t comm_barrier(mps_solver* s)
+{
+	MPS_TRY(s->comm.ext.ensure(2ull * s->comm.nranks + 2, s->stream));
+	MPS_NCCL(s, g_nccl.AllReduce(s->comm.ext.p, s->comm.ext.p, 1, ncclUint64, ncclSum, comm_of(s), s->stream));
+	return cudaStreamSynchronize(s->stream);
+}
+
+void close_peers(mps_solver* s)
+{
+	Comm& c = s->comm;
+	for (int r = 0; r < kMaxPeerRanks; r++)
+	{
+		if (c.peer_base[r]) cudaIpcCloseMemHandle(c.peer_base[r]);
+		c.peer_base[r] = nullptr; c.peer_arena[r] = nullptr;
+	}
+}
+
+} // namespace
+
+void comm_release_peers(mps_solver* s)
+{
+	Comm& c = s->comm;
+	if (!c.arena) return;
+	close_peers(s);
+	if (c.on && c.peer_mode == 1) comm_barrier(s); // nobody frees memory a peer still maps
+	cudaFree(c.arena);
+	c.arena = nullptr; c.arena_bytes = 0; c.arena_rows = 0;
+	if (s->cg.z_borrowed) { s->cg.z0.p = nullptr; s->cg.z0.cap = 0; s->cg.z1.p = nullptr; s->cg.z1.cap = 0; s->cg.z_borrowed = false; }
+}
+
+// The arena of this rank for `rows` rows: (re)allocated when it is too small — every rank holds the same particle count, so all
+// of them take this branch in the same step — and exchanged with the other ranks: IPC handles travel through an NCCL
+// all-gather of a small device buffer, peers map them with cudaIpcOpenMemHandle (which also enables peer access).
+// If any rank cannot export or map (no P2P, IPC disabled in the container) all ranks agree on the NCCL stepwise solve.
+cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows)
+{
+	Comm& c = s->comm;
+	CgBuffers& cg = s->cg;
+	cudaStream_t st = s->stream;
+	if (c.arena && rows <= c.arena_rows) return cudaSuccess;
+	const int R = c.nranks;
+	if (c.arena)
+	{
+		MPS_TRY(cudaStreamSynchronize(st));
+		comm_release_peers(s);
+	}
+	if (!cg.z_borrowed) { cg.z0.release(); cg.z1.release(); }
+	const uint64_t want_rows = rows + rows / 4 + 16;
+	size_t bytes = arena_size(want_rows);
+	bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+	void* mem = nullptr;
+	MPS_TRY(cudaMalloc(&mem, bytes));
+	MPS_TRY(cudaMemsetAsync(mem, 0, bytes, st));
+	c.arena = static_cast<unsigned char*>(mem); c.arena_bytes = bytes; c.arena_rows = want_rows;
+	cg.z0.p = reinterpret_cast<double*>(c.arena + kPeerHeaderBytes); cg.z0.cap = 2 * want_rows;
+	cg.z1.p = cg.z0.p + 2 * want_rows; cg.z1.cap = 2 * want_rows;
+	cg.z_borrowed = true;
+
+	PeerExport mine{};
+	mine.bytes = bytes;
+	const bool want_peer = (R <= kMaxPeerRanks) && !std::getenv("MPS_COMM_NCCL_ONLY");
+	if (want_peer && allocation_offset(mem, &mine.offset) && cudaIpcGetMemHandle(&mine.handle, mem) == cudaSuccess) mine.ok = 1;
+	cudaGetLastError(); // a failed export is not an error of the solver: it selects the NCCL path
+	static_assert(sizeof(PeerExport) % 8 == 0, "exchanged as 64-bit words");
+	DevBuf<unsigned long long> xchg;
+	const size_t words = sizeof(PeerExport) / 8;
+	MPS_TRY(xchg.ensure(words * (R + 1), st));
+	MPS_TRY(cudaMemcpyAsync(xchg.p + words * R, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+	MPS_NCCL(s, g_nccl.AllGather(xchg.p + words * R, xchg.p, words, ncclUint64, comm_of(s), st));
+	std::vector<PeerExport> all(R);
+	MPS_TRY(cudaMemcpyAsync(all.data(), xchg.p, sizeof(PeerExport) * R, cudaMemcpyDeviceToHost, st));
+	MPS_TRY(cudaStreamSynchronize(st));
+	xchg.release();
+	s->stats.comm_calls += 1;
+
+	unsigned long long ok = 1;
+	for (int r = 0; r < R; r++) ok &= all[r].ok;
+	if (ok)
+	{
+		for (int r = 0; r < R && ok; r++)
+		{
+			if (r == c.rank) { c.peer_arena[r] = c.arena; continue; }
+			void* base = nullptr;
+			if (cudaIpcOpenMemHandle(&base, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+			c.peer_base[r] = base;
+			c.peer_arena[r] = static_cast<unsigned char*>(base) + all[r].offset;
+		}
+	}
+	// agree: one rank that cannot map sends everybody to the NCCL path
+	unsigned long long* flag = c.ext.p; // ensured by comm_barrier / halo_extents sizes; make sure here
+	MPS_TRY(c.ext.ensure(2ull * R + 2, st));
+	flag = c.ext.p;
+	MPS_TRY(cudaMemcpyAsync(flag, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
+	MPS_NCCL(s, g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclMin, comm_of(s), st));
+	MPS_TRY(cudaMemcpyAsync(&ok, flag, sizeof(ok), cudaMemcpyDeviceToHost, st));
+	MPS_TRY(cudaStreamSynchronize(st));
+	s->stats.comm_calls += 1;
+	if (!ok) close_peers(s);
+	c.peer_mode = ok ? 1 : 2;
+	return cudaSuccess;
+}
+
+// comm.link for the next persistent solve: neighbours' {r, p} buffers, our rows that they read, everybody's mailbox
+cudaError_t comm_prepare_link(mps_solver* s)
+{
+	Comm& c = s->comm;
+	const int k = c.rank, R = c.nranks;
+	std::vector<unsigned long long> ext;
+	MPS_TRY(halo_extents(s, ext));
+	const Slab me = slab_of(s, k);
+	auto clampu = [](uint64_t v, uint64_t lo, uint64_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+	PeerLink& L = c.link;
+	L = PeerLink{};
+	L.rank = k; L.nranks = R;
+	c.solves += 1;
+	L.tag = c.solves << 32;
+	const size_t z1_off = kPeerHeaderBytes + 2ull * c.arena_rows * sizeof(double);
+	for (int side = 0; side < 2; side++)
+	{
+		const int nb = (side == 0) ? k - 1 : k + 1;
+		L.exp_b[side] = L.exp_e[side] = 0;
+		if (nb < 0 || nb >= R) continue;
+		L.nb_z0[side] = reinterpret_cast<double2*>(c.peer_arena[nb] + kPeerHeaderBytes);
+		L.nb_z1[side] = reinterpret_cast<double2*>(c.peer_arena[nb] + z1_off);
+		if (side == 0) { L.exp_b[0] = me.b; L.exp_e[0] = clampu(ext[2 * nb + 1], me.b, me.e); } // the left rank reads my first rows
+		else { L.exp_b[1] = clampu(ext[2 * nb], me.b, me.e); L.exp_e[1] = me.e; }              // the right rank reads my last rows
+	}
+	for (int r = 0; r < R; r++) L.mail[r] = reinterpret_cast<PeerMail*>(c.peer_arena[r]);
+	return cudaSuccess;
+}
+
 // Computer::SolvePressurePoissonEquation (Computer.hpp:1359-1429) across ranks: the same CG, the same stopping rule; one
 // launch per phase so that the dot products can be all-reduced and the rim of {r, p} exchanged between them.
 cudaError_t comm_cg_solve(mps_solver* s)
 {
 	CgBuffers& c = s->cg;
 	cudaStream_t st = s->stream;
-	const int R = s->comm.nranks;
 	MPS_TRY(c.step.ensure(1, st));
 	if (!c.h_step) MPS_TRY(cudaMallocHost(&c.h_step, sizeof(CgStepScalars)));
 	MPS_TRY(cudaMemsetAsync(c.step.p, 0, sizeof(CgStepScalars), st));
 
-	// halo extents of every rank (once per solve: the chunks were rebuilt by this step's assembly)
-	MPS_TRY(s->comm.ext.ensure(2ull * R + 2, st));
-	unsigned long long* ext_local = s->comm.ext.p + 2ull * R;
-	const unsigned long long init[2] = { s->own0(), s->own1() };
-	MPS_TRY(cudaMemcpyAsync(ext_local, init, sizeof(init), cudaMemcpyHostToDevice, st));
-	k_halo_extent<<<64, 256, 0, st>>>(c.desc.p, s->d_sc, ext_local);
-	s->stats.kernel_launches += 1;
-	MPS_NCCL(s, g_nccl.AllGather(ext_local, s->comm.ext.p, 2, ncclUint64, comm_of(s), st));
-	std::vector<unsigned long long> ext(2ull * R);
-	MPS_TRY(cudaMemcpyAsync(ext.data(), s->comm.ext.p, 2ull * R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	MPS_TRY(cudaStreamSynchronize(st));
-	for (int k = 0; k < R; k++)
-	{
-		// a window must not reach past the adjacent slab (slabs thinner than one cell column are not supported)
-		const uint64_t lo_ok = (k > 0) ? static_cast<uint64_t>(k - 1) * s->slab() : 0;
-		const uint64_t hi_ok = (k + 1 < R) ? std::min<uint64_t>(static_cast<uint64_t>(k + 2) * s->slab(), s->n) : s->n;
-		if (ext[2 * k] < lo_ok || ext[2 * k + 1] > hi_ok + 1 /* window ends are rounded up to even */) { s->comm_error = "slab thinner than the neighbour stencil: use fewer GPUs for this problem"; return cudaErrorUnknown; }
-	}
+	std::vector<unsigned long long> ext;
+	MPS_TRY(halo_extents(s, ext));
 
 	double* z0 = c.z0.p;
 	double* z1 = c.z1.p;
@@ -245,6 +420,13 @@ int mps_comm_info(mps_handle s, int* rank, int* nranks, uint64_t* own_first, uin
 	if (nranks) *nranks = s->comm.on ? s->comm.nranks : 1;
 	if (own_first) *own_first = s->own0();
 	if (own_last) *own_last = s->own1();
+	return MPS_OK;
+}
+
+int mps_comm_mode(mps_handle s, int* mode)
+{
+	if (!s || !mode) return MPS_BAD_ARG;
+	*mode = s->comm.on ? s->comm.peer_mode : 0;
 	return MPS_OK;
 }
 

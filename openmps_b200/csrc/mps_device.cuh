@@ -115,6 +115,23 @@ struct CgStepScalars
 	int zcur_is_1;
 };
 
+// ---- multi-GPU persistent CG over peer memory (mps_cg.cu k_cg_stream<LPR, true>, mps_comm.cu) ---------------------------
+constexpr int kMaxPeerRanks = 8;
+struct alignas(16) PeerMail { double value; unsigned long long flag; };  // one rank's contribution to one reduction
+// layout of one rank's shared arena (one cudaMalloc, exported with cudaIpcGetMemHandle): [mail 4 x kMaxPeerRanks][z0][z1]
+constexpr size_t kPeerMailBytes = 4 * kMaxPeerRanks * sizeof(PeerMail);
+constexpr size_t kPeerHeaderBytes = 1024; // the mailbox, padded
+static_assert(kPeerMailBytes <= kPeerHeaderBytes, "arena header");
+struct PeerLink
+{
+	int rank, nranks;
+	unsigned long long tag;          // solve number << 32: flags of earlier solves never match
+	double2* nb_z0[2];               // [0] left, [1] right neighbour's z0 (peer-mapped), nullptr at the ends of the chain
+	double2* nb_z1[2];
+	uint64_t exp_b[2], exp_e[2];     // own rows [b, e) that the left / right neighbour's windows reach (empty if b >= e)
+	PeerMail* mail[kMaxPeerRanks];   // every rank's mailbox (peer-mapped; mail[rank] is local)
+};
+
 template<int D>
 struct Particles
 {

@@ -58,6 +58,7 @@ struct CgBuffers
 	DevBuf<double> z0, z1;   // streaming kernel: {r_i, p_i} interleaved (2 doubles per row), ping-pong
 	DevBuf<double> partials; // 2 x max grid size
 	bool external = false;   // loaded through mps_set_system (not assembled from particles)
+	bool z_borrowed = false; // z0 / z1 point into the multi-GPU peer arena (mps_comm.cu) and are not owned by the DevBufs
 
 	// chunk-blob form of the assembled system (mps_device.cuh, mps_chunk.cu); rowptr above is still produced (row lengths
 	// for inspection, nnz), col / val are only used by externally loaded systems
@@ -87,6 +88,17 @@ struct Comm
 	int rank = 0, nranks = 1;
 	void* nccl = nullptr;     // ncclComm_t
 	DevBuf<unsigned long long> ext;  // halo extents of all ranks (2 per rank), device
+
+	// peer-memory coupling of the persistent CG kernel (mps_comm.cu comm_peer_*): one arena per rank
+	// [mailbox | z0 | z1], exported with cudaIpcGetMemHandle and mapped by every other rank
+	int peer_mode = 0;                 // 0 not decided yet, 1 peer memory (persistent kernel), 2 NCCL stepwise (IPC unavailable)
+	unsigned char* arena = nullptr;    // this rank's arena
+	size_t arena_bytes = 0;
+	uint64_t arena_rows = 0;           // rows the z sections are sized for
+	unsigned char* peer_arena[8] = {}; // peers' arenas mapped into this process ([rank] = arena)
+	void* peer_base[8] = {};           // what cudaIpcOpenMemHandle returned (to close)
+	unsigned long long solves = 0;     // persistent solves so far (tag of the mailbox flags)
+	PeerLink link{};                   // what the next solve's kernel gets
 };
 } // namespace mps
 
@@ -185,6 +197,9 @@ cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
 // mps_comm.cu
 cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden = false); // no-op without a communicator
 cudaError_t comm_cg_solve(mps_solver* s);                                       // multi-rank CG (stepwise kernels + NCCL)
+cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows);                    // (re)allocates + exchanges the peer arenas; sets cg.z0 / cg.z1
+cudaError_t comm_prepare_link(mps_solver* s);                                   // halo extents -> comm.link for the next persistent solve
+void comm_release_peers(mps_solver* s);
 // mps_scan.cu
 cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /* n + 1 */, uint64_t n, DevBuf<uint64_t>& tmp, cudaStream_t st,
 	uint64_t* launches);

@@ -28,11 +28,11 @@ def main():
     dist.broadcast(uid, 0)
     g = capi.GpuComputer.from_scene(sc, device=local)
     g.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
-    info = g.comm_info()
     g.forward(steps)
+    info = g.comm_info()
     st = g.state()
     stats = g.stats_dict()
-    out = {"rank": rank, "own": info["own"], "n": sc.count, "iters": stats["cg_iterations"], "comm_calls": stats.get("comm_calls")}
+    out = {"rank": rank, "own": info["own"], "n": sc.count, "iters": stats["cg_iterations"], "comm_calls": stats.get("comm_calls"), "mode": info["mode"]}
     if rank == 0:
         ref = capi.GpuComputer.from_scene(sc, device=local)
         ref.forward(steps)

@@ -73,17 +73,24 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("coupling", ["peer-memory", "nccl"])
 @pytest.mark.parametrize("scene,steps", [("dambreak2d", 5), ("static", 3), ("dambreak3d", 2)])
-def test_two_gpus_match_one_gpu(scene, steps):
+def test_two_gpus_match_one_gpu(scene, steps, coupling):
+    """The slab-decomposed step on 2 GPUs == the 1-GPU step, for both couplings of the CG iteration: the persistent kernel
+    over NVLink peer memory (the default where the ranks can map each other's memory) and NCCL between per-phase launches."""
     if _gpu_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ)
+    if coupling == "nccl":
+        env["MPS_COMM_NCCL_ONLY"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29612", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), scene, str(steps)],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     rows = [json.loads(l[5:]) for l in r.stdout.splitlines() if l.startswith("MGPU ")]
     assert len(rows) == 2
     r0 = next(x for x in rows if x["rank"] == 0)
+    assert all(x["mode"] == coupling for x in rows), [x["mode"] for x in rows]
     assert all(x["replicas_equal"] for x in rows)
     assert r0["type_equal"]
     # only the summation order of the CG dot products differs between 1 and 2 GPUs

@@ -16,8 +16,8 @@ block.  Workload at N = 1: BASELINE.json configs[1], the 2-D Koshizuka & Oka dam
   cpu_baseline (N = 1, rank 0): the reference's own CPU code (oracle/_ref, OpenMP, all host cores) on ONE step of the
             same 1M-particle workload (~10-30 s)
 
---impl reference times the reference's CPU implementation (oracle/_ref if present, else the CPU restatement) for K steps
-on a bounded sample of the workload (a coarser dam break; the sample is named in cpu_baseline.sample).
+--impl reference times the reference's CPU implementation (oracle/_ref if present, else the CPU restatement) on the same
+workload, bounded in wall-clock time (cpu_baseline.sample says how many steps were timed).
 N > 1: one process per GPU (torchrun); the SAME block is cut into N x-slabs of the cell-sorted slots (strong scaling):
 every rank computes the neighbour lists, gather stages, PPE rows and CG rows of its slab; NCCL all-gathers the fields
 neighbours read after each stage, and the CG iteration runs as ONE persistent kernel per rank coupled over NVLink peer
@@ -55,7 +55,8 @@ WORKLOADS = {
     "dambreak3d_1m": (lambda: scenes.dambreak3d(3.6e-3), "DamBreak 3D l0=3.6e-3"),
     "dambreak3d_10m": (lambda: scenes.dambreak3d(1.36e-3), "DamBreak 3D l0=1.36e-3, ~12.2M particles (~10M fluid)"),
 }
-REFERENCE_SAMPLE = "dambreak2d_72k"   # bounded sample for --impl reference (a 1M step costs ~30 s of CPU)
+REFERENCE_SAMPLE = "dambreak2d_72k"   # fallback block when only the scalar CPU restatement is available
+REFERENCE_BUDGET_S = 150              # wall-clock bound of the --impl reference loop
 
 
 def read_peaks():
@@ -80,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -118,26 +119,37 @@ def dist_info():
 
 
 def reference_arm(args, rank, world):
-    """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    """The reference's own CPU implementation of the path on the host cores (rank 0 only), on the SAME workload as our arm.
+    Bounded: a 1M-particle ForwardTime() costs ~9 s on 16 cores, so the timed loop stops after K steps or REFERENCE_BUDGET_S
+    seconds, whichever comes first; `steps` in the line is what was actually timed."""
     if rank != 0:
         return 0
     from oracle import bind
-    name = args.workload if args.workload_forced else REFERENCE_SAMPLE
+    name = args.workload
     sc = WORKLOADS[name][0]()
     use_ref = bind.available(sc.env.dim, sc.env.central_gravity, fast=True)
+    if not use_ref and sc.count > 200000:
+        name = REFERENCE_SAMPLE          # the scalar restatement cannot do a 1M step in bounded time: coarser block, said in `sample`
+        sc = WORKLOADS[name][0]()
     eng = bind.RefComputer.from_scene(sc, fast=True) if use_ref else bind.PortComputer.from_scene(sc)
     kind = "reference" if use_ref else "port"
-    cores = NPROC if use_ref else min(NPROC, int(os.environ["OMP_NUM_THREADS"]))
-    eng.forward(args.warmup)
+    cores = NPROC if use_ref else 1
+    t_start = time.perf_counter()
+    warm = 0
+    while warm < args.warmup and time.perf_counter() - t_start < REFERENCE_BUDGET_S / 3:
+        eng.forward(1); warm += 1
     t0 = time.perf_counter()
-    eng.forward(args.steps)
+    steps = 0
+    while steps < args.steps and (steps == 0 or time.perf_counter() - t_start < REFERENCE_BUDGET_S):
+        eng.forward(1); steps += 1
     sec = time.perf_counter() - t0
     alive = int((eng.state()["type"] != 3).sum())
-    value = alive * args.steps / sec
-    sample = f"{WORKLOADS[name][1]}: N={sc.count}, {args.steps} steps after {args.warmup} warm-up steps from rest"
+    value = alive * steps / sec
+    sample = (f"{WORKLOADS[name][1]}: N={sc.count}, {steps} ForwardTime() steps after {warm} warm-up steps from rest "
+              f"(asked {args.steps}/{args.warmup}; bounded to {REFERENCE_BUDGET_S} s), OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}")
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "particles": sc.count, "description": WORKLOADS[name][1], "host": "CPU only (OpenMP)"},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
@@ -222,12 +234,15 @@ def main():
     snap = gpu.state()
     snap_t = gpu.time()
     gpu.reset_stats()
-    sampler = ClockSampler(local)
+    # clocks / throttle reasons of rank 0's GPU during the timed region (one nvidia-smi poller: the ranks run in lockstep, and a
+    # poller per rank stalls every GPU in turn)
+    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     dev_ms = gpu.run_steps(args.steps)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     st = gpu.stats_dict()
     alive = int((gpu.state()["type"] != 3).sum())
 

@@ -270,7 +270,7 @@ int mps_destroy(mps_handle s)
 	s->cg.rowptr.release(); s->cg.col.release(); s->cg.val.release(); s->cg.b.release(); s->cg.x.release(); s->cg.r.release();
 	s->cg.p0.release(); s->cg.p1.release(); s->cg.ap.release(); s->cg.partials.release(); s->cg.z0.release(); s->cg.z1.release();
 	s->cg.blk_chunks.release(); s->cg.blk_bytes.release(); s->cg.chunk_of_row.release(); s->cg.chunk_base.release();
-	s->cg.blob_base.release(); s->cg.blk_cost.release(); s->cg.cost_base.release(); s->cg.desc.release(); s->cg.blobs.release(); s->cg.prof.release();
+	s->cg.blob_base.release(); s->cg.blk_cost.release(); s->cg.cost_base.release(); s->cg.cta_frac.release(); s->cg.cta_speed.release(); s->cg.cta_meas.release(); s->cg.desc.release(); s->cg.live.release(); s->cg.blk_live.release(); s->cg.live_base.release(); s->cg.blobs.release(); s->cg.prof.release();
 	s->stage_d.release(); s->stage_i.release(); s->flush.release();
 	if (s->d_sc) cudaFree(s->d_sc);
 	if (s->h_sc) cudaFreeHost(s->h_sc);

@@ -22,6 +22,7 @@
 // columns of neighbouring rows overlap).  bench.py reports achieved = K * (12 nnz + 92 rows) / kernel time, the
 // figure SURVEY.md §8d defines.
 #include <cstdlib>
+#include <vector>
 
 #include <cooperative_groups.h>
 
@@ -215,9 +216,8 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_solve(CgArgs a)
 struct CgStreamArgs
 {
 	uint64_t n;
-	const ChunkDesc* desc;
+	const ChunkDesc* desc;     // the chunks that have entries (CgBuffers::live), a.sc->n_live of them
 	const unsigned char* blobs;
-	const uint32_t* chunk_of_row; // row -> chunk (bounds the chunks of the rows this rank owns)
 	const double* b;
 	double* x;
 	double2* z0;               // {r_i, p_i} interleaved, ping-pong pair: ONE window copy per range brings both gathered vectors
@@ -231,6 +231,8 @@ struct CgStreamArgs
 	uint32_t stages;
 	int l2_stream;             // blobs do not fit L2: stream them evict_first
 	unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (mps_get_cg_profile), nullptr = off
+	const double* cta_frac;    // [gridDim.x + 1] cumulative cost share of the CTAs (load balance, k_cg_rebalance)
+	unsigned long long* cta_meas; // [2][gridDim.x] {cost taken, SpMV cycles} of this solve, or nullptr
 	uint64_t own0, own1;       // rows this rank updates ([0, n) on one GPU)
 	PeerLink peer;             // multi-GPU persistent solve (k_cg_stream<LPR, true>): neighbours' buffers and mailboxes over NVLink
 };
@@ -290,41 +292,40 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 //   * the rim of {r, p}: the part of a chunk's window that lies in a neighbour rank's slab is fetched by the producer warp
 //     straight from that rank's buffer (the same bulk async copy, peer address as its source: the transfer rides the ring
 //     of stages like any other window copy, NVLink latency hidden by the look-ahead); nobody keeps copies of foreign rows;
-//   * the two dot products per iteration: CTA 0 of every rank sums its grid's partials and stores {sum, sequence flag} into
-//     the mailbox of every rank, its own included (value first, flag with release.sys); every CTA of every rank waits for
-//     the flags of all ranks in its own rank's mailbox and adds the values in rank order (the same order everywhere: every
-//     CTA of every rank gets the same bits and takes the same convergence decision).
-//   The exchange doubles as the grid barrier and as the cross-GPU barrier that orders the rim reads after the owner's writes
-//   (a thread that writes a row a neighbour reads fences at system scope before its CTA arrives).
+//   * the two dot products per iteration: CTA 0 of every rank sums its grid's partials, stores {sum, sequence flag} into the
+//     mailbox of every rank, its own included (one 16-byte store of self-validating words), waits for the flags of all ranks
+//     in its own mailbox, adds the values in rank order (the same order everywhere: every rank gets the same bits and takes the
+//     same convergence decision) and publishes the total to the other CTAs of its grid, which poll a local flag.
+//   The exchange doubles as the grid barrier and as the cross-GPU barrier that orders the rim reads after the owner's writes:
+//   writer -> CTA arrival (release.gpu) -> CTA 0 (acquire.gpu) -> mailbox word over NVLink -> reader; the rows themselves
+//   never leave the owner's L2, which is where the neighbour's bulk copies read them.
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+__device__ __forceinline__ void st_relaxed_sys_v2(void* p, unsigned long long a, unsigned long long b)
+{
+	asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_v2(const void* p, unsigned long long& a, unsigned long long& b)
+{
+	asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p)
 {
 	unsigned long long v;
-	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v)
-{
-	asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // A peer that never arrives (a rank that died) must end as a trapped launch, never as a hung GPU: waits are bounded in time.
 constexpr unsigned long long kPeerWaitNs = 30ull * 1000ull * 1000ull * 1000ull;
-
-// is `row` (one of this rank's) inside a neighbour rank's windows?  Its {r, p} is then read by that rank over NVLink, so the
-// thread that wrote it fences at system scope before its CTA arrives at the next reduction
-__device__ __forceinline__ bool exposed_row(const PeerLink& pl, const uint64_t row)
-{
-	return (row >= pl.exp_b[0] && row < pl.exp_e[0]) || (row >= pl.exp_b[1] && row < pl.exp_e[1]);
-}
 
 // Sum of `local` over every thread of every CTA of every rank; `seq` counts the reductions of this solve.  One GPU: per-CTA
 // partials, grid barrier, every CTA adds the partials in the same fixed order.  Multi-GPU: see above.
@@ -343,52 +344,72 @@ __device__ __forceinline__ double all_sum(const CgStreamArgs& a, double local, d
 	seq++;
 	const unsigned long long want = pl.tag | seq;
 	const unsigned slot = static_cast<unsigned>(seq & 3ull);
+	PeerMail* bc = pl.mail[pl.rank] + 4 * kMaxPeerRanks + slot; // the total, published by CTA 0 to the other CTAs of this grid
 	if (threadIdx.x < 32)
 	{
 		const unsigned lane = threadIdx.x;
+		double total = 0.0;
 		if (blockIdx.x != 0)
 		{
 			if (lane == 0)
 			{
 				part[blockIdx.x] = local;
 				async::red_release_gpu_add(&a.sc->grid_barrier, 1ull);
+				// cheap polls (relaxed), one acquire fence once the flag is there
+				const unsigned long long t0 = globaltimer_ns();
+				for (unsigned spin = 0; ld_relaxed_gpu(&bc->flag) != want; spin++)
+					if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > kPeerWaitNs) __trap();
+				fence_acq_rel_gpu();
+				total = __ldcg(&bc->value);
 			}
 		}
 		else
 		{
-			// CTA 0: wait for the other CTAs of this grid, add the partials in a fixed order, send the sum to every rank
+			// CTA 0: wait for the other CTAs of this grid, add the partials in a fixed order, exchange the sum with the other ranks
 			bar_target += nblocks - 1;
 			if (lane == 0)
 			{
 				part[0] = local;
-				for (unsigned spin = 0; async::ld_acquire_gpu(&a.sc->grid_barrier) < bar_target; spin++)
+				for (unsigned spin = 0; ld_relaxed_gpu(&a.sc->grid_barrier) < bar_target; spin++)
 					if (spin > (1u << 27)) __trap();
+				fence_acq_rel_gpu();
 			}
 			__syncwarp();
 			double v = 0.0;
 			for (unsigned k = lane; k < nblocks; k += 32) v += __ldcg(part + k);
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			double mine = 0.0;
 			if (lane < static_cast<unsigned>(pl.nranks))
 			{
-				// my sum into everybody's mailbox (my own included): value, then the flag with release semantics at system scope
+				// My sum into everybody's mailbox (my own included) as ONE 16-byte store of two self-validating words, each
+				// {32 bits of the value, 32-bit sequence flag} — the flag-in-data scheme of NCCL's LL protocol: an aligned 8-byte
+				// word is never torn, so a reader that sees both flags has the whole value, and no system-scope fence sits on the
+				// critical path (a fence.sys costs more than the NVLink flight).  Ordering of the rim rows needs none either:
+				// they were in this GPU's L2 before their writers' arrivals were counted above, and the neighbours read them
+				// from that L2 (peer addresses are not cached on the reading side) after they have seen this flag.
+				const unsigned long long f32 = ((pl.tag >> 32) & 0xffull) << 24 | (seq & 0xffffffull);
+				const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
 				PeerMail* out = pl.mail[lane] + slot * kMaxPeerRanks + pl.rank;
-				st_relaxed_sys_f64(&out->value, v);
-				st_release_sys(&out->flag, want);
+				st_relaxed_sys_v2(out, (bits & 0xffffffffull) | (f32 << 32), (bits >> 32) | (f32 << 32));
+				const PeerMail* in = pl.mail[pl.rank] + slot * kMaxPeerRanks + lane;
+				const unsigned long long t0 = globaltimer_ns();
+				unsigned long long w0 = 0, w1 = 0;
+				for (unsigned spin = 0;; spin++)
+				{
+					ld_relaxed_sys_v2(in, w0, w1);
+					if ((w0 >> 32) == f32 && (w1 >> 32) == f32) break;
+					if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > kPeerWaitNs) __trap();
+				}
+				mine = __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+			}
+			for (int r = 0; r < pl.nranks; r++) total += __shfl_sync(0xffffffffu, mine, r); // rank order: identical bits on every rank
+			if (lane == 0)
+			{
+				bc->value = total;
+				st_release_gpu(&bc->flag, want);
 			}
 		}
-		// every CTA: the sums of all ranks arrive in this rank's mailbox; add them in rank order (identical bits on every rank)
-		double mine = 0.0;
-		if (lane < static_cast<unsigned>(pl.nranks))
-		{
-			const PeerMail* in = pl.mail[pl.rank] + slot * kMaxPeerRanks + lane;
-			const unsigned long long t0 = globaltimer_ns();
-			for (unsigned spin = 0; ld_acquire_sys(&in->flag) != want; spin++)
-				if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > kPeerWaitNs) __trap();
-			mine = __ldcg(&in->value);
-		}
-		double total = 0.0;
-		for (int r = 0; r < pl.nranks; r++) total += __shfl_sync(0xffffffffu, mine, r);
 		if (lane == 0) red[0] = total;
 	}
 	__syncthreads();
@@ -514,7 +535,6 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 		const unsigned group = warp / gwarps;
 		const unsigned ctid = threadIdx.x - group * gwarps * 32, nct = gwarps * 32;
 		const uint32_t lr = ctid / LPR, sl = ctid % LPR;
-		bool pushed = false;
 		for (uint32_t q = group; q < live; q += kGroups)
 		{
 			const uint32_t k = it + q;
@@ -582,14 +602,12 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 				{
 					const double ri = a.b[row] - acc;
 					zcur[row] = make_double2(ri, 0.0);
-					if (MG) pushed |= exposed_row(a.peer, row);
 					local = fma(ri, ri, local);
 				}
 			}
 			__syncwarp();
 			if (lane == 0) async::mbar_arrive(&sm.empty[s]); // this warp is done reading stage s
 		}
-		if (MG && pushed) __threadfence_system(); // rim rows are visible at system scope before this CTA's arrival is seen
 	}
 	it += live;
 	return local;
@@ -623,64 +641,64 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 	sm.empty = sm.full + S;
 	sm.dfull = sm.empty + S;
 	c.red = reinterpret_cast<double*>(sm.dfull + 2);                          // kMaxStreamWarps + 1
-	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(c.red + kMaxStreamWarps + 1); // row0, row1
-	uint32_t* ctl = reinterpret_cast<uint32_t*>(ctl64 + 2);                    // c0, c1, live chunks
+	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(c.red + kMaxStreamWarps + 1); // row0, row1, zero0, zero1
+	uint32_t* ctl = reinterpret_cast<uint32_t*>(ctl64 + 4);                    // c0, c1
 
-	const uint64_t n = a.n;
 	const unsigned nblocks = gridDim.x;
 	if (threadIdx.x == 0)
 	{
 		for (uint32_t s = 0; s < S; s++) { async::mbar_init(&sm.full[s], 1u); async::mbar_init(&sm.empty[s], cwarps / kGroups); }
 		async::mbar_init(&sm.dfull[0], 1u); async::mbar_init(&sm.dfull[1], 1u);
 		async::mbar_init_fence();
-		// this CTA's run of chunks: split the modelled cost evenly (descriptors hold its exclusive prefix)
-		const uint64_t nchunks = a.sc->n_chunks, total = a.sc->cost_total;
-		// multi-GPU: only the chunks that hold rows of this rank (all others are empty here and would only be walked over)
-		const uint64_t chunk_lo = (a.own1 > a.own0) ? a.chunk_of_row[a.own0] : 0;
-		const uint64_t chunk_hi = (a.own1 > a.own0) ? a.chunk_of_row[a.own1 - 1] + 1ull : 0;
+		// this CTA's run of the chunks that have entries: split the modelled cost evenly (descriptors hold its exclusive prefix).
+		// Chunks without entries (runs of Dummy / Disabled rows; on several GPUs all the other ranks' rows) are not in the list.
+		const uint64_t nlive = a.sc->n_live, total = a.sc->cost_total;
 		uint32_t bound[2];
 		for (int w = 0; w < 2; w++)
 		{
 			const uint64_t b = blockIdx.x + w;
-			if (b >= nblocks) { bound[w] = static_cast<uint32_t>(chunk_hi); continue; }
-			const uint64_t target = total / nblocks * b + (total % nblocks) * b / nblocks;
-			uint64_t lo = 0, hi = nchunks; // first chunk with cost_off >= target
+			if (b >= nblocks) { bound[w] = static_cast<uint32_t>(nlive); continue; }
+			const uint64_t target = static_cast<uint64_t>(static_cast<double>(total) * a.cta_frac[b]);
+			uint64_t lo = 0, hi = nlive; // first chunk with cost_off >= target
 			while (lo < hi)
 			{
 				const uint64_t mid = (lo + hi) >> 1;
 				if (a.desc[mid].cost_off < target) lo = mid + 1; else hi = mid;
 			}
-			bound[w] = static_cast<uint32_t>(lo < chunk_lo ? chunk_lo : (lo > chunk_hi ? chunk_hi : lo));
+			bound[w] = static_cast<uint32_t>(lo);
 		}
-		ctl[0] = bound[0]; ctl[1] = bound[1]; ctl[2] = 0;
-		uint64_t r0 = (bound[0] < nchunks) ? a.desc[bound[0]].row_begin : n;
-		uint64_t r1 = (bound[1] < nchunks) ? a.desc[bound[1]].row_begin : n;
-		// rows of other ranks (multi-GPU) are never updated here
-		r0 = r0 < a.own0 ? a.own0 : (r0 > a.own1 ? a.own1 : r0);
-		r1 = r1 < a.own0 ? a.own0 : (r1 > a.own1 ? a.own1 : r1);
-		ctl64[0] = r0; ctl64[1] = r1;
+		ctl[0] = bound[0]; ctl[1] = bound[1];
+		// rows this CTA updates in phase 2: an even share of the rows this rank owns — phase 2 is row-local, so its split is
+		// independent of who multiplied which chunk (its loads go to L2: another CTA wrote p and Ap)
+		const uint64_t own = a.own1 - a.own0;
+		ctl64[0] = a.own0 + (own / nblocks) * blockIdx.x + (own % nblocks) * blockIdx.x / nblocks;
+		ctl64[1] = a.own0 + (own / nblocks) * (blockIdx.x + 1ull) + (own % nblocks) * (blockIdx.x + 1ull) / nblocks;
+		// rows this CTA zeroes before the first phase: from its first chunk to the next CTA's first chunk (the same CTA then writes
+		// the residual of the rows that have entries; together the CTAs cover every row this rank owns)
+		uint64_t z0r = (blockIdx.x == 0) ? a.own0 : ((bound[0] < nlive) ? a.desc[bound[0]].row_begin : a.own1);
+		uint64_t z1r = (blockIdx.x + 1 == nblocks) ? a.own1 : ((bound[1] < nlive) ? a.desc[bound[1]].row_begin : a.own1);
+		ctl64[2] = z0r < a.own0 ? a.own0 : (z0r > a.own1 ? a.own1 : z0r);
+		ctl64[3] = z1r < a.own0 ? a.own0 : (z1r > a.own1 ? a.own1 : z1r);
+		if (a.cta_meas)
+		{
+			const uint64_t cb = (bound[0] < nlive) ? a.desc[bound[0]].cost_off : total, ce = (bound[1] < nlive) ? a.desc[bound[1]].cost_off : total;
+			a.cta_meas[blockIdx.x] = ce - cb;
+		}
 	}
 	__syncthreads();
 	c.c0 = ctl[0]; c.c1 = ctl[1];
 	c.row0 = ctl64[0]; c.row1 = ctl64[1];
+	c.live = c.c1 - c.c0;
 	{
-		// chunks with entries (the others are skipped by every phase) ; rows of this CTA start from zero everywhere
-		uint32_t mine = 0;
-		for (uint32_t k = c.c0 + threadIdx.x; k < c.c1; k += nthreads) mine += (a.desc[k].nnz != 0) ? 1u : 0u;
-		if (mine) atomicAdd(&ctl[2], mine);
 		if (ZERO_ROWS)
 		{
-			bool pushed = false;
-			for (uint64_t i = c.row0 + threadIdx.x; i < c.row1; i += nthreads)
+			for (uint64_t i = ctl64[2] + threadIdx.x; i < ctl64[3]; i += nthreads)
 			{
 				a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0;
-				if (MG) pushed |= exposed_row(a.peer, i);
 			}
-			if (MG && pushed) __threadfence_system();
 		}
 	}
 	__syncthreads();
-	c.live = ctl[2];
 	c.pol_matrix = a.l2_stream ? async::policy_evict_first() : async::policy_evict_normal();
 	c.pol_vector = a.l2_stream ? async::policy_evict_last() : async::policy_evict_normal();
 	return c;
@@ -693,7 +711,6 @@ __device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint6
 {
 	const unsigned nthreads = blockDim.x;
 	double local = 0.0;
-	bool pushed = false;
 	for (uint64_t base = row0 + threadIdx.x; base < row1; base += 4ull * nthreads)
 	{
 		double pv[4], xv[4], av[4], rv[4];
@@ -702,7 +719,8 @@ __device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint6
 		{
 			const uint64_t i = base + static_cast<uint64_t>(q) * nthreads;
 			const bool on = i < row1;
-			pv[q] = on ? zcur[i].y : 0.0; xv[q] = on ? a.x[i] : 0.0; av[q] = on ? a.ap[i] : 0.0; rv[q] = on ? zprev[i].x : 0.0;
+			// L2 loads: p and Ap of these rows were written by whichever CTA multiplied their chunk
+			pv[q] = on ? __ldcg(&zcur[i].y) : 0.0; xv[q] = on ? __ldcg(a.x + i) : 0.0; av[q] = on ? __ldcg(a.ap + i) : 0.0; rv[q] = on ? __ldcg(&zprev[i].x) : 0.0;
 		}
 #pragma unroll
 		for (int q = 0; q < 4; q++)
@@ -713,12 +731,10 @@ __device__ __forceinline__ double update_rows(const CgStreamArgs& a, const uint6
 				a.x[i] = fma(alpha, pv[q], xv[q]);
 				const double ri = fma(-alpha, av[q], rv[q]);
 				zcur[i].x = ri;
-				if (MG) pushed |= exposed_row(a.peer, i); // the finished {r', p} of a rim row
 				local = fma(ri, ri, local);
 			}
 		}
 	}
-	if (MG && pushed) __threadfence_system();
 	return local;
 }
 
@@ -739,6 +755,8 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	unsigned long long bar_target = 0, seq = 0;
 	uint32_t it = 0, dseq = 0;
 	const bool prof_on = (a.prof != nullptr) && (threadIdx.x == 0);
+	const bool meas_on = (a.cta_meas != nullptr) && (threadIdx.x == 0);
+	unsigned long long spmv_cycles = 0;
 
 	// ---- r0 = b - A x ; p_prev = 0 ; rr = r0.r0 (Computer.hpp:1382-1386) ----
 	double local = spmv_phase<LPR, false, MG>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
@@ -754,9 +772,10 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 	while (iter < n && !converged)
 	{
 		// ---- phase 1: p = r + beta p_prev ; Ap = A p ; p.Ap ----
-		const long long t0 = prof_on ? clock64() : 0;
+		const long long t0 = (prof_on || meas_on) ? clock64() : 0;
 		local = spmv_phase<LPR, true, MG>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
-		const long long t1 = prof_on ? clock64() : 0;
+		const long long t1 = (prof_on || meas_on) ? clock64() : 0;
+		spmv_cycles += static_cast<unsigned long long>(t1 - t0);
 		const double pAp = all_sum<MG>(a, local, part1, red, bar_target, seq, nblocks);
 		const long long t2 = prof_on ? clock64() : 0;
 		const double alpha = rr / pAp;
@@ -784,6 +803,7 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 		rr = rr_new;
 	}
 
+	if (meas_on) a.cta_meas[nblocks + blockIdx.x] = spmv_cycles; // what k_cg_rebalance turns into the next solve's split
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
 		a.sc->z_final = (zprev == a.z1) ? 1 : 0;
@@ -792,6 +812,47 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 		a.sc->rr = rr;
 		a.sc->cg_converged = converged ? 1 : 0;
 		if (!converged) atomicMax(&a.sc->error, static_cast<int>(MPS_CG_NOT_CONVERGED)); // Computer.hpp:1424-1428
+	}
+}
+
+// Load balance of the next solve from this solve's own counters.  The cost model (ChunkLimits::cost_*) cannot know everything
+// that makes a chunk slow (row-length spread, where its window lives, which SM runs the CTA), so every CTA reports the modelled
+// cost it took and the cycles its SpMV phases needed; the smoothed cost-per-cycle of CTA b decides how much modelled cost it
+// gets next time.  One block; meas = [cost taken x grid][cycles x grid].
+__global__ void __launch_bounds__(256) k_cg_rebalance(const unsigned long long* __restrict__ meas, double* __restrict__ speed, double* __restrict__ frac,
+	const unsigned nblocks)
+{
+	__shared__ double sp[256];
+	__shared__ double tot[2];
+	const unsigned b = threadIdx.x;
+	const double cost = (b < nblocks) ? static_cast<double>(meas[b]) : 0.0;
+	const double cyc = (b < nblocks) ? static_cast<double>(meas[nblocks + b]) : 0.0;
+	const bool ok = (cost > 0.0) && (cyc > 0.0);
+	sp[b] = ok ? cost : 0.0;
+	__syncthreads();
+	if (b == 0) { double t = 0.0; for (unsigned k = 0; k < nblocks; k++) t += sp[k]; tot[0] = t; }
+	__syncthreads();
+	sp[b] = ok ? cyc : 0.0;
+	__syncthreads();
+	if (b == 0) { double t = 0.0; for (unsigned k = 0; k < nblocks; k++) t += sp[k]; tot[1] = t; }
+	__syncthreads();
+	double v = (b < nblocks) ? speed[b] : 0.0;
+	if (ok && tot[0] > 0.0 && tot[1] > 0.0)
+	{
+		double rel = (cost / cyc) / (tot[0] / tot[1]);
+		rel = rel < 0.5 ? 0.5 : (rel > 2.0 ? 2.0 : rel);
+		v = 0.5 * v + 0.5 * rel;
+	}
+	if (b < nblocks) speed[b] = v;
+	sp[b] = v;
+	__syncthreads();
+	if (b == 0)
+	{
+		double t = 0.0;
+		for (unsigned k = 0; k < nblocks; k++) t += sp[k];
+		double run = 0.0;
+		for (unsigned k = 0; k < nblocks; k++) { frac[k] = run / t; run += sp[k]; }
+		frac[nblocks] = 1.0;
 	}
 }
 
@@ -865,7 +926,7 @@ StreamGeometry stream_geometry(const ChunkLimits& lim)
 	g.blob_stage_bytes = round_up(chunk_blob_bytes(lim.max_rows, lim.max_nnz), 128);
 	g.window_stage = round_up(lim.max_window, 16);
 	g.stage_bytes = g.blob_stage_bytes + 24u * g.window_stage;
-	g.fixed_bytes = 2u * kDescBatch * sizeof(ChunkDesc) + 2u * 8u * 8u /* barriers, <= 8 stages */ + 16u + (kMaxStreamWarps + 1) * 8u + 16u + 16u;
+	g.fixed_bytes = 2u * kDescBatch * sizeof(ChunkDesc) + 2u * 8u * 8u /* barriers, <= 8 stages */ + 16u + (kMaxStreamWarps + 1) * 8u + 32u + 16u;
 	return g;
 }
 
@@ -886,13 +947,27 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 	L.grid = static_cast<unsigned>(s->sm_count); // one CTA per SM: the ring wants the whole shared memory
 	cudaError_t e = c.partials.ensure(2ull * L.grid + 8, s->stream);
 	if (e != cudaSuccess) return e;
+	if (!c.cta_frac.p)
+	{
+		// uniform split until the kernel has measured itself
+		if ((e = c.cta_frac.ensure(L.grid + 1, s->stream)) != cudaSuccess) return e;
+		if ((e = c.cta_speed.ensure(L.grid, s->stream)) != cudaSuccess) return e;
+		if ((e = c.cta_meas.ensure(2ull * L.grid, s->stream)) != cudaSuccess) return e;
+		std::vector<double> f(L.grid + 1), one(L.grid, 1.0);
+		for (unsigned b = 0; b <= L.grid; b++) f[b] = static_cast<double>(b) / L.grid;
+		if ((e = cudaMemcpyAsync(c.cta_frac.p, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) return e;
+		if ((e = cudaMemcpyAsync(c.cta_speed.p, one.data(), one.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) return e;
+		if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return e; // the host vectors go out of scope
+		if (const char* v = std::getenv("MPS_CG_ADAPTIVE")) c.adaptive = std::atoi(v) != 0;
+	}
 	CgStreamArgs& a = L.a;
-	a.n = c.n; a.desc = c.desc.p; a.blobs = c.blobs.p; a.chunk_of_row = c.chunk_of_row.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
+	a.n = c.n; a.desc = c.live.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
 	a.ap = c.ap.p; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
 	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
 	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
 	a.l2_stream = ((s->nbr_total + (s->own1() - s->own0())) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
 	a.prof = nullptr;
+	a.cta_frac = c.cta_frac.p; a.cta_meas = nullptr;
 	a.own0 = s->own0(); a.own1 = s->own1();
 	a.peer = PeerLink{};
 	return cudaSuccess;
@@ -928,9 +1003,22 @@ cudaError_t launch_stream(mps_solver* s)
 		L.a.prof = c.prof.p;
 		c.prof_blocks = L.grid;
 	}
+	if (c.adaptive)
+	{
+		e = cudaMemsetAsync(c.cta_meas.p, 0, 2ull * L.grid * sizeof(unsigned long long), s->stream);
+		if (e != cudaSuccess) return e;
+		L.a.cta_meas = c.cta_meas.p;
+	}
 	void* params[] = { &L.a };
 	s->stats.kernel_launches += 1;
-	return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR, MG>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_cg_stream<LPR, MG>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	if (e != cudaSuccess) return e;
+	if (c.adaptive)
+	{
+		k_cg_rebalance<<<1, 256, 0, s->stream>>>(c.cta_meas.p, c.cta_speed.p, c.cta_frac.p, L.grid);
+		s->stats.kernel_launches += 1;
+	}
+	return cudaGetLastError();
 }
 
 template<bool MG>

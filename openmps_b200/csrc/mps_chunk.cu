@@ -8,7 +8,7 @@
 // One thread partitions one block of 256 consecutive rows greedily: a chunk grows while rows <= max_rows,
 // entries <= max_nnz and window <= max_window.  Pass 1 (EMIT = false) counts chunks and blob bytes per block, a scan
 // turns them into offsets, pass 2 (EMIT = true) repeats the same walk and writes descriptors, the row -> chunk map and
-// the 16-bit row offsets inside each blob.  Integer work, ~N x 6 B read + N x 6 B written; negligible next to the solve.
+// the 16-bit row offsets inside each blob, plus the compacted list of the chunks that have entries (what the CG kernel walks).  Integer work, ~N x 6 B read + N x 6 B written; negligible next to the solve.
 #include "mps_solver.h"
 
 namespace mps {
@@ -76,9 +76,10 @@ struct Open
 };
 
 template<int D, bool EMIT>
-__device__ __forceinline__ void close_chunk(const Open& o, uint32_t& n_chunks, uint64_t& bytes, uint64_t& cost, const uint64_t chunk_base,
-	const uint64_t blob_base, const uint64_t cost_base, const ChunkLimits& lim,
-	const uint32_t* __restrict__ row_len, ChunkDesc* __restrict__ desc, uint32_t* __restrict__ chunk_of_row, unsigned char* __restrict__ blobs)
+__device__ __forceinline__ void close_chunk(const Open& o, uint32_t& n_chunks, uint32_t& n_live, uint64_t& bytes, uint64_t& cost, const uint64_t chunk_base,
+	const uint64_t blob_base, const uint64_t cost_base, const uint64_t live_base, const ChunkLimits& lim,
+	const uint32_t* __restrict__ row_len, ChunkDesc* __restrict__ desc, ChunkDesc* __restrict__ live, uint32_t* __restrict__ chunk_of_row,
+	unsigned char* __restrict__ blobs)
 {
 	const uint32_t bb = chunk_blob_bytes(o.rows, o.nnz);
 	if (EMIT)
@@ -101,6 +102,7 @@ __device__ __forceinline__ void close_chunk(const Open& o, uint32_t& n_chunks, u
 			if (on) off += o.win.len[k];
 		}
 		desc[id] = d;
+		if (o.nnz) live[live_base + n_live] = d;
 		*reinterpret_cast<ChunkDesc*>(blobs + d.blob_off) = d; // blob header
 		uint16_t* rowoff = reinterpret_cast<uint16_t*>(blobs + d.blob_off + kBlobHeader + static_cast<uint64_t>(round_up8(o.nnz)) * 10u);
 		uint32_t run = 0;
@@ -114,28 +116,29 @@ __device__ __forceinline__ void close_chunk(const Open& o, uint32_t& n_chunks, u
 	}
 	n_chunks += 1;
 	bytes += bb;
-	if (o.nnz) cost += lim.cost_fixed + lim.cost_per_nnz * o.nnz;
+	if (o.nnz) { n_live += 1; cost += lim.cost_fixed + lim.cost_per_nnz * o.nnz; }
 }
 
 template<int D, bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_chunk_build(uint64_t n, const uint32_t* __restrict__ row_len, const uint32_t* __restrict__ skey,
 	const uint64_t* __restrict__ cell_start, EnvConst env, ChunkLimits lim, uint32_t* __restrict__ blk_chunks, uint32_t* __restrict__ blk_bytes,
-	uint32_t* __restrict__ blk_cost, const uint64_t* __restrict__ chunk_base, const uint64_t* __restrict__ blob_base,
-	const uint64_t* __restrict__ cost_base, ChunkDesc* __restrict__ desc, uint64_t desc_cap,
-	uint32_t* __restrict__ chunk_of_row, unsigned char* __restrict__ blobs, DevScalars* sc)
+	uint32_t* __restrict__ blk_cost, uint32_t* __restrict__ blk_live, const uint64_t* __restrict__ chunk_base, const uint64_t* __restrict__ blob_base,
+	const uint64_t* __restrict__ cost_base, const uint64_t* __restrict__ live_base, ChunkDesc* __restrict__ desc, ChunkDesc* __restrict__ live,
+	uint64_t desc_cap, uint32_t* __restrict__ chunk_of_row, unsigned char* __restrict__ blobs, DevScalars* sc)
 {
 	const uint64_t blk = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	const uint64_t r0 = blk * kBlockRows;
 	if (r0 >= n) return;
 	const uint64_t r1 = (r0 + kBlockRows < n) ? r0 + kBlockRows : n;
 	const uint64_t cbase = EMIT ? chunk_base[blk] : 0, bbase = EMIT ? blob_base[blk] : 0, kbase = EMIT ? cost_base[blk] : 0;
+	const uint64_t lbase = EMIT ? live_base[blk] : 0;
 	if (EMIT && chunk_base[blk + 1] > desc_cap)
 	{
 		// cannot happen with the capacity the host allocates unless almost every row needs a chunk of its own
 		atomicMax(&sc->error, static_cast<int>(MPS_CUDA_ERROR));
 		return;
 	}
-	uint32_t n_chunks = 0;
+	uint32_t n_chunks = 0, n_live = 0;
 	uint64_t bytes = 0, cost = 0;
 	Open o;
 	o.row_begin = static_cast<uint32_t>(r0); o.rows = 0; o.nnz = 0; o.c_a = -1; o.c_b = -1; o.win.n = 0; o.win.total = 0; o.first_active = 0;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_build(uint64_t n, const uint
 		const bool fits = (o.rows + 1 <= lim.max_rows) && (o.nnz + len <= lim.max_nnz) && (win.total <= lim.max_window);
 		if (!fits && o.rows > 0)
 		{
-			close_chunk<D, EMIT>(o, n_chunks, bytes, cost, cbase, bbase, kbase, lim, row_len, desc, chunk_of_row, blobs);
+			close_chunk<D, EMIT>(o, n_chunks, n_live, bytes, cost, cbase, bbase, kbase, lbase, lim, row_len, desc, live, chunk_of_row, blobs);
 			o.row_begin = static_cast<uint32_t>(r); o.rows = 0; o.nnz = 0; o.c_a = -1; o.c_b = -1; o.win.n = 0; o.win.total = 0;
 			c_a = -1; c_b = -1;
 			if (len > 0)
@@ -173,14 +176,15 @@ __global__ void __launch_bounds__(kThreads) k_chunk_build(uint64_t n, const uint
 		}
 		o.rows += 1; o.nnz += len; o.c_a = c_a; o.c_b = c_b; o.win = win; o.first_active = first_active;
 	}
-	if (o.rows > 0) close_chunk<D, EMIT>(o, n_chunks, bytes, cost, cbase, bbase, kbase, lim, row_len, desc, chunk_of_row, blobs);
-	if (!EMIT) { blk_chunks[blk] = n_chunks; blk_bytes[blk] = static_cast<uint32_t>(bytes); blk_cost[blk] = static_cast<uint32_t>(cost); }
+	if (o.rows > 0) close_chunk<D, EMIT>(o, n_chunks, n_live, bytes, cost, cbase, bbase, kbase, lbase, lim, row_len, desc, live, chunk_of_row, blobs);
+	if (!EMIT) { blk_chunks[blk] = n_chunks; blk_bytes[blk] = static_cast<uint32_t>(bytes); blk_cost[blk] = static_cast<uint32_t>(cost); blk_live[blk] = n_live; }
 }
 
 __global__ void k_chunk_totals(const uint64_t* __restrict__ chunk_base, const uint64_t* __restrict__ blob_base, const uint64_t* __restrict__ cost_base,
-	uint64_t nblk, DevScalars* sc)
+	const uint64_t* __restrict__ live_base, uint64_t nblk, DevScalars* sc)
 {
 	sc->n_chunks = chunk_base[nblk];
+	sc->n_live = live_base[nblk];
 	sc->blob_total = blob_base[nblk];
 	sc->cost_total = cost_base[nblk];
 }
@@ -198,23 +202,25 @@ cudaError_t build(mps_solver* s)
 	MPS_TRY(cg.blk_chunks.ensure(nblk + 1, st)); MPS_TRY(cg.blk_bytes.ensure(nblk + 1, st));
 	MPS_TRY(cg.chunk_base.ensure(nblk + 2, st)); MPS_TRY(cg.blob_base.ensure(nblk + 2, st));
 	MPS_TRY(cg.blk_cost.ensure(nblk + 1, st)); MPS_TRY(cg.cost_base.ensure(nblk + 2, st));
+	MPS_TRY(cg.blk_live.ensure(nblk + 1, st)); MPS_TRY(cg.live_base.ensure(nblk + 2, st));
 	MPS_TRY(cg.chunk_of_row.ensure(n, st));
 	// capacities that need no host round trip: entries <= neighbour entries + n; every chunk pads < 16 + 16 + 16 bytes
 	const uint64_t desc_cap = n / 16 + nblk + 1024;
-	MPS_TRY(cg.desc.ensure(desc_cap, st));
+	MPS_TRY(cg.desc.ensure(desc_cap, st)); MPS_TRY(cg.live.ensure(desc_cap, st));
 	const uint64_t blob_cap = (s->nbr_total + n) * 10 + n * 2 + desc_cap * (96 + kBlobHeader) + 256;
 	MPS_TRY(cg.blobs.ensure(blob_cap, st));
 	cg.desc_cap = desc_cap;
 
 	k_chunk_build<D, false><<<grid, kThreads, 0, st>>>(n, s->row_len.p, s->skey.p, s->cell_start.p, s->env, cg.limits, cg.blk_chunks.p,
-		cg.blk_bytes.p, cg.blk_cost.p, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, s->d_sc);
+		cg.blk_bytes.p, cg.blk_cost.p, cg.blk_live.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, s->d_sc);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_chunks.p, cg.chunk_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_bytes.p, cg.blob_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_cost.p, cg.cost_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
-	k_chunk_build<D, true><<<grid, kThreads, 0, st>>>(n, s->row_len.p, s->skey.p, s->cell_start.p, s->env, cg.limits, nullptr, nullptr, nullptr,
-		cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.desc.p, desc_cap, cg.chunk_of_row.p, cg.blobs.p, s->d_sc);
-	k_chunk_totals<<<1, 1, 0, st>>>(cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, nblk, s->d_sc);
+	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_live.p, cg.live_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
+	k_chunk_build<D, true><<<grid, kThreads, 0, st>>>(n, s->row_len.p, s->skey.p, s->cell_start.p, s->env, cg.limits, nullptr, nullptr, nullptr, nullptr,
+		cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.live_base.p, cg.desc.p, cg.live.p, desc_cap, cg.chunk_of_row.p, cg.blobs.p, s->d_sc);
+	k_chunk_totals<<<1, 1, 0, st>>>(cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.live_base.p, nblk, s->d_sc);
 	s->stats.kernel_launches += 2;
 	return cudaGetLastError();
 }

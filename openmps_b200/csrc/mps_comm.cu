@@ -65,6 +65,20 @@ struct Nccl
 
 Nccl g_nccl;
 
+struct PeerBarrierArgs
+{
+	int rank, nranks;
+	unsigned long long seq;
+	unsigned long long* flags[kMaxPeerRanks]; // every rank's arrival counters (peer-mapped), [r][k] = arrivals of rank k seen by rank r
+};
+struct PeerGatherArgs
+{
+	int rank, nranks, nfields;
+	unsigned long long* dst[4];
+	const unsigned long long* src[4][kMaxPeerRanks];
+	unsigned long long slab_words[4], total_words[4];
+};
+
 #define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
 #define MPS_NCCL(s, expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) { (s)->comm_error = std::string(#expr ": ") + g_nccl.GetErrorString(r_); return cudaErrorUnknown; } } while (0)
 
@@ -157,32 +171,36 @@ cudaError_t halo_exchange(mps_solver* s, double* z, const std::vector<unsigned l
 
 } // namespace
 
-cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden)
-{
-	if (!s->comm.on || s->n == 0) return cudaSuccess;
-	const uint64_t m = s->slab();
-	const int vs = s->vec_stride();
-	const int k = s->comm.rank;
-	if (pos) { double* p = s->pos[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
-	if (vel) { double* p = s->vel[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
-	if (prs) { double* p = s->prs[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
-	if (nden) { double* p = s->nden[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
-	s->stats.comm_calls += (pos ? 1 : 0) + (vel ? 1 : 0) + (prs ? 1 : 0) + (nden ? 1 : 0);
-	return cudaSuccess;
-}
-
 // ---- peer-memory coupling of the persistent CG kernel ----------------------------------------------------------------------
 namespace {
 
 inline size_t arena_size(uint64_t rows) { return kPeerHeaderBytes + 2ull * rows * sizeof(double2); }
 
+bool allocation_offset(void* p, unsigned long long* offset);
+
 struct PeerExport
 {
-	cudaIpcMemHandle_t handle; // of the allocation that contains the arena
-	unsigned long long offset; // arena base - allocation base (cudaMalloc may sub-allocate small requests)
+	cudaIpcMemHandle_t handle; // of the allocation that contains the buffer
+	unsigned long long offset; // buffer - allocation base (cudaMalloc may sub-allocate small requests)
 	unsigned long long bytes;
 	unsigned long long ok;     // 0: this rank could not export
 };
+constexpr int kExports = 9;    // the arena + pos[2], vel[2], prs[2], nden[2]
+
+inline void state_pointers(mps_solver* s, const void* out[8])
+{
+	for (int b = 0; b < 2; b++) { out[0 + b] = s->pos[b].p; out[2 + b] = s->vel[b].p; out[4 + b] = s->prs[b].p; out[6 + b] = s->nden[b].p; }
+}
+
+bool export_buffer(void* p, PeerExport& e)
+{
+	e.ok = 0;
+	if (!p) return false;
+	if (!allocation_offset(p, &e.offset)) return false;
+	if (cudaIpcGetMemHandle(&e.handle, static_cast<unsigned char*>(p) - e.offset) != cudaSuccess) { cudaGetLastError(); return false; }
+	e.ok = 1;
+	return true;
+}
 
 // offset of `p` inside its allocation (the IPC handle always opens the allocation's base)
 bool allocation_offset(void* p, unsigned long long* offset)
@@ -217,6 +235,11 @@ void close_peers(mps_solver* s)
 	{
 		if (c.peer_base[r]) cudaIpcCloseMemHandle(c.peer_base[r]);
 		c.peer_base[r] = nullptr; c.peer_arena[r] = nullptr;
+		for (int f = 0; f < 8; f++)
+		{
+			if (c.peer_state_base[r][f]) cudaIpcCloseMemHandle(c.peer_state_base[r][f]);
+			c.peer_state_base[r][f] = nullptr; c.peer_state[r][f] = nullptr;
+		}
 	}
 }
 
@@ -233,68 +256,93 @@ void comm_release_peers(mps_solver* s)
 	if (s->cg.z_borrowed) { s->cg.z0.p = nullptr; s->cg.z0.cap = 0; s->cg.z1.p = nullptr; s->cg.z1.cap = 0; s->cg.z_borrowed = false; }
 }
 
-// The arena of this rank for `rows` rows: (re)allocated when it is too small — every rank holds the same particle count, so all
-// of them take this branch in the same step — and exchanged with the other ranks: IPC handles travel through an NCCL
-// all-gather of a small device buffer, peers map them with cudaIpcOpenMemHandle (which also enables peer access).
-// If any rank cannot export or map (no P2P, IPC disabled in the container) all ranks agree on the NCCL stepwise solve.
+// What the other ranks read of this one, shared through CUDA IPC: the arena for `rows` rows (mailbox, barrier flags, {r, p}
+// buffers of the CG kernel) and the replicated state arrays.  (Re)done when the arena is too small or a state array was
+// re-allocated — every rank holds the same particles, so all of them take this branch in the same step.  IPC handles travel
+// through an NCCL all-gather of a small device buffer; peers map them with cudaIpcOpenMemHandle (which enables peer access).
+// If any rank cannot export or map (no P2P, IPC disabled in the container) all ranks agree on the NCCL paths.
 cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows)
 {
 	Comm& c = s->comm;
 	CgBuffers& cg = s->cg;
 	cudaStream_t st = s->stream;
-	if (c.arena && rows <= c.arena_rows) return cudaSuccess;
+	const void* now[8];
+	state_pointers(s, now);
+	bool same = c.arena && rows <= c.arena_rows;
+	for (int f = 0; f < 8 && same; f++) same = (now[f] == c.exported[f]);
+	if (same) return cudaSuccess;
 	const int R = c.nranks;
-	if (c.arena)
+	const bool regrow = !c.arena || rows > c.arena_rows;
+	MPS_TRY(cudaStreamSynchronize(st));
+	if (c.arena && regrow) comm_release_peers(s);
+	else if (c.arena) { close_peers(s); if (c.peer_mode == 1) MPS_TRY(comm_barrier(s)); }
+	if (regrow)
 	{
-		MPS_TRY(cudaStreamSynchronize(st));
-		comm_release_peers(s);
+		if (!cg.z_borrowed) { cg.z0.release(); cg.z1.release(); }
+		const uint64_t want_rows = rows + rows / 4 + 16;
+		size_t bytes = arena_size(want_rows);
+		bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+		void* mem = nullptr;
+		MPS_TRY(cudaMalloc(&mem, bytes));
+		MPS_TRY(cudaMemsetAsync(mem, 0, bytes, st));
+		c.arena = static_cast<unsigned char*>(mem); c.arena_bytes = bytes; c.arena_rows = want_rows;
+		cg.z0.p = reinterpret_cast<double*>(c.arena + kPeerHeaderBytes); cg.z0.cap = 2 * want_rows;
+		cg.z1.p = cg.z0.p + 2 * want_rows; cg.z1.cap = 2 * want_rows;
+		cg.z_borrowed = true;
+		c.bar_seq = 0; // the new arena's flags start from zero on every rank
 	}
-	if (!cg.z_borrowed) { cg.z0.release(); cg.z1.release(); }
-	const uint64_t want_rows = rows + rows / 4 + 16;
-	size_t bytes = arena_size(want_rows);
-	bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
-	void* mem = nullptr;
-	MPS_TRY(cudaMalloc(&mem, bytes));
-	MPS_TRY(cudaMemsetAsync(mem, 0, bytes, st));
-	c.arena = static_cast<unsigned char*>(mem); c.arena_bytes = bytes; c.arena_rows = want_rows;
-	cg.z0.p = reinterpret_cast<double*>(c.arena + kPeerHeaderBytes); cg.z0.cap = 2 * want_rows;
-	cg.z1.p = cg.z0.p + 2 * want_rows; cg.z1.cap = 2 * want_rows;
-	cg.z_borrowed = true;
+	for (int f = 0; f < 8; f++) c.exported[f] = now[f];
 
-	PeerExport mine{};
-	mine.bytes = bytes;
+	PeerExport mine[kExports] = {};
 	const bool want_peer = (R <= kMaxPeerRanks) && !std::getenv("MPS_COMM_NCCL_ONLY");
-	if (want_peer && allocation_offset(mem, &mine.offset) && cudaIpcGetMemHandle(&mine.handle, mem) == cudaSuccess) mine.ok = 1;
+	if (want_peer)
+	{
+		export_buffer(c.arena, mine[0]);
+		for (int f = 0; f < 8; f++) export_buffer(const_cast<void*>(now[f]), mine[1 + f]);
+	}
 	cudaGetLastError(); // a failed export is not an error of the solver: it selects the NCCL path
 	static_assert(sizeof(PeerExport) % 8 == 0, "exchanged as 64-bit words");
 	DevBuf<unsigned long long> xchg;
-	const size_t words = sizeof(PeerExport) / 8;
+	const size_t words = sizeof(mine) / 8;
 	MPS_TRY(xchg.ensure(words * (R + 1), st));
-	MPS_TRY(cudaMemcpyAsync(xchg.p + words * R, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+	MPS_TRY(cudaMemcpyAsync(xchg.p + words * R, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
 	MPS_NCCL(s, g_nccl.AllGather(xchg.p + words * R, xchg.p, words, ncclUint64, comm_of(s), st));
-	std::vector<PeerExport> all(R);
-	MPS_TRY(cudaMemcpyAsync(all.data(), xchg.p, sizeof(PeerExport) * R, cudaMemcpyDeviceToHost, st));
+	std::vector<PeerExport> all(static_cast<size_t>(R) * kExports);
+	MPS_TRY(cudaMemcpyAsync(all.data(), xchg.p, sizeof(mine) * R, cudaMemcpyDeviceToHost, st));
 	MPS_TRY(cudaStreamSynchronize(st));
 	xchg.release();
 	s->stats.comm_calls += 1;
 
 	unsigned long long ok = 1;
-	for (int r = 0; r < R; r++) ok &= all[r].ok;
-	if (ok)
+	for (size_t k = 0; k < all.size(); k++) ok &= all[k].ok;
+	for (int r = 0; r < R && ok; r++)
 	{
-		for (int r = 0; r < R && ok; r++)
+		const PeerExport* e = &all[static_cast<size_t>(r) * kExports];
+		if (r == c.rank)
 		{
-			if (r == c.rank) { c.peer_arena[r] = c.arena; continue; }
+			c.peer_arena[r] = c.arena;
+			for (int f = 0; f < 8; f++) c.peer_state[r][f] = static_cast<unsigned char*>(const_cast<void*>(now[f]));
+			continue;
+		}
+		// one allocation may hold several of the buffers (cudaMalloc sub-allocates small requests): open every handle once
+		void* opened[kExports] = {};
+		for (int k = 0; k < kExports && ok; k++)
+		{
 			void* base = nullptr;
-			if (cudaIpcOpenMemHandle(&base, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-			c.peer_base[r] = base;
-			c.peer_arena[r] = static_cast<unsigned char*>(base) + all[r].offset;
+			for (int j = 0; j < k; j++) if (std::memcmp(&e[j].handle, &e[k].handle, sizeof(cudaIpcMemHandle_t)) == 0) { base = opened[j]; break; }
+			if (!base)
+			{
+				if (cudaIpcOpenMemHandle(&base, e[k].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+				if (k == 0) c.peer_base[r] = base; else c.peer_state_base[r][k - 1] = base;
+			}
+			opened[k] = base;
+			unsigned char* ptr = static_cast<unsigned char*>(base) + e[k].offset;
+			if (k == 0) c.peer_arena[r] = ptr; else c.peer_state[r][k - 1] = ptr;
 		}
 	}
 	// agree: one rank that cannot map sends everybody to the NCCL path
-	unsigned long long* flag = c.ext.p; // ensured by comm_barrier / halo_extents sizes; make sure here
 	MPS_TRY(c.ext.ensure(2ull * R + 2, st));
-	flag = c.ext.p;
+	unsigned long long* flag = c.ext.p;
 	MPS_TRY(cudaMemcpyAsync(flag, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
 	MPS_NCCL(s, g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclMin, comm_of(s), st));
 	MPS_TRY(cudaMemcpyAsync(&ok, flag, sizeof(ok), cudaMemcpyDeviceToHost, st));
@@ -305,6 +353,109 @@ cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows)
 	return cudaSuccess;
 }
 
+// ---- the per-stage all-gather of replicated fields over peer memory ------------------------------------------------------
+namespace {
+
+// Stream-level barrier across the ranks (one warp): my arrival number into every rank's flag array, then wait for everybody's.
+// Launched between kernels: what the previous kernels of this stream wrote is complete and sits in this GPU's L2.
+__global__ void k_peer_barrier(PeerBarrierArgs a)
+{
+	const unsigned lane = threadIdx.x;
+	if (lane < static_cast<unsigned>(a.nranks))
+	{
+		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flags[lane] + a.rank), "l"(a.seq) : "memory");
+		unsigned long long v = 0, t0 = 0, t1 = 0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		for (unsigned spin = 0;; spin++)
+		{
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags[a.rank] + lane) : "memory");
+			if (v >= a.seq) break;
+			if ((spin & 1023u) == 1023u)
+			{
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+				if (t1 - t0 > 30ull * 1000ull * 1000ull * 1000ull) __trap(); // a dead rank ends as a failed launch, not as a hung GPU
+			}
+		}
+		asm volatile("fence.acq_rel.sys;" ::: "memory");
+	}
+}
+
+// every rank pulls the other ranks' slabs of up to four fields straight from their memory (8-byte words, coalesced)
+__global__ void __launch_bounds__(256) k_peer_gather(PeerGatherArgs a)
+{
+	const unsigned long long tid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (int f = 0; f < a.nfields; f++)
+	{
+		const unsigned long long slab = a.slab_words[f], total = a.total_words[f];
+		unsigned long long* __restrict__ dst = a.dst[f];
+		for (int r = 0; r < a.nranks; r++)
+		{
+			if (r == a.rank) continue;
+			const unsigned long long b = static_cast<unsigned long long>(r) * slab;
+			unsigned long long e = b + slab;
+			if (e > total) e = total;
+			const unsigned long long* __restrict__ src = a.src[f][r];
+			for (unsigned long long i = b + tid; i < e; i += nthreads) dst[i] = src[i];
+		}
+	}
+}
+
+cudaError_t peer_barrier(mps_solver* s)
+{
+	Comm& c = s->comm;
+	PeerBarrierArgs a{};
+	a.rank = c.rank; a.nranks = c.nranks; a.seq = ++c.bar_seq;
+	for (int r = 0; r < c.nranks; r++) a.flags[r] = reinterpret_cast<unsigned long long*>(c.peer_arena[r] + kPeerBarrierOff);
+	k_peer_barrier<<<1, 32, 0, s->stream>>>(a);
+	s->stats.kernel_launches += 1;
+	return cudaGetLastError();
+}
+
+} // namespace
+
+// Fields that neighbours read, after the stage that wrote this rank's slab of them.  Peer memory: barrier (every rank's slab
+// is written), one kernel in which every rank copies the other slabs straight from their owners over NVLink, barrier (nobody
+// overwrites a slab a peer is still reading).  NCCL all-gathers where the ranks cannot map each other's memory.
+cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden)
+{
+	if (!s->comm.on || s->n == 0) return cudaSuccess;
+	Comm& c = s->comm;
+	const uint64_t m = s->slab();
+	const int vs = s->vec_stride();
+	const int k = c.rank;
+	MPS_TRY(comm_ensure_arena(s, s->n + 64)); // first use (or re-allocated state): exchange the IPC handles
+	if (c.peer_mode == 1)
+	{
+		PeerGatherArgs a{};
+		a.rank = k; a.nranks = c.nranks;
+		auto add = [&](int field, uint64_t words_per_row)
+		{
+			const int f = 2 * field + s->cur, q = a.nfields++;
+			a.dst[q] = reinterpret_cast<unsigned long long*>(c.peer_state[k][f]);
+			for (int r = 0; r < c.nranks; r++) a.src[q][r] = reinterpret_cast<const unsigned long long*>(c.peer_state[r][f]);
+			a.slab_words[q] = m * words_per_row; a.total_words[q] = s->n * words_per_row;
+		};
+		if (pos) add(0, vs);
+		if (vel) add(1, vs);
+		if (prs) add(2, 1);
+		if (nden) add(3, 1);
+		if (a.nfields == 0) return cudaSuccess;
+		MPS_TRY(peer_barrier(s));
+		k_peer_gather<<<2 * s->sm_count, 256, 0, s->stream>>>(a);
+		s->stats.kernel_launches += 1;
+		MPS_TRY(peer_barrier(s));
+		c.peer_gathers += 1;
+		return cudaGetLastError();
+	}
+	if (pos) { double* p = s->pos[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
+	if (vel) { double* p = s->vel[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
+	if (prs) { double* p = s->prs[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
+	if (nden) { double* p = s->nden[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
+	s->stats.comm_calls += (pos ? 1 : 0) + (vel ? 1 : 0) + (prs ? 1 : 0) + (nden ? 1 : 0);
+	return cudaSuccess;
+}
+
 // comm.link for the next persistent solve: neighbours' {r, p} buffers, our rows that they read, everybody's mailbox
 cudaError_t comm_prepare_link(mps_solver* s)
 {
@@ -312,8 +463,6 @@ cudaError_t comm_prepare_link(mps_solver* s)
 	const int k = c.rank, R = c.nranks;
 	std::vector<unsigned long long> ext;
 	MPS_TRY(halo_extents(s, ext));
-	const Slab me = slab_of(s, k);
-	auto clampu = [](uint64_t v, uint64_t lo, uint64_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
 	PeerLink& L = c.link;
 	L = PeerLink{};
 	L.rank = k; L.nranks = R;
@@ -323,12 +472,9 @@ cudaError_t comm_prepare_link(mps_solver* s)
 	for (int side = 0; side < 2; side++)
 	{
 		const int nb = (side == 0) ? k - 1 : k + 1;
-		L.exp_b[side] = L.exp_e[side] = 0;
 		if (nb < 0 || nb >= R) continue;
 		L.nb_z0[side] = reinterpret_cast<double2*>(c.peer_arena[nb] + kPeerHeaderBytes);
 		L.nb_z1[side] = reinterpret_cast<double2*>(c.peer_arena[nb] + z1_off);
-		if (side == 0) { L.exp_b[0] = me.b; L.exp_e[0] = clampu(ext[2 * nb + 1], me.b, me.e); } // the left rank reads my first rows
-		else { L.exp_b[1] = clampu(ext[2 * nb], me.b, me.e); L.exp_e[1] = me.e; }              // the right rank reads my last rows
 	}
 	for (int r = 0; r < R; r++) L.mail[r] = reinterpret_cast<PeerMail*>(c.peer_arena[r]);
 	return cudaSuccess;

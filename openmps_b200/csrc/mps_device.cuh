@@ -60,6 +60,7 @@ struct DevScalars
 	unsigned int disabled_now;      // particles disabled by the last search
 	unsigned long long active_rows; // PPE rows of the last assembly that are not Dummy / Disabled
 	unsigned long long n_chunks;    // chunks of the last assembly
+	unsigned long long n_live;      // ... of which have matrix entries (the list the CG kernel walks)
 	unsigned long long blob_total;  // bytes of all chunk blobs of the last assembly
 	unsigned long long cost_total;  // sum of the chunk cost model (load balance of the CG kernel)
 	unsigned long long grid_barrier; // arrival counter of the CG kernel's grid barrier (zeroed before each launch)
@@ -118,17 +119,18 @@ struct CgStepScalars
 // ---- multi-GPU persistent CG over peer memory (mps_cg.cu k_cg_stream<LPR, true>, mps_comm.cu) ---------------------------
 constexpr int kMaxPeerRanks = 8;
 struct alignas(16) PeerMail { double value; unsigned long long flag; };  // one rank's contribution to one reduction
-// layout of one rank's shared arena (one cudaMalloc, exported with cudaIpcGetMemHandle): [mail 4 x kMaxPeerRanks][z0][z1]
+// layout of one rank's shared arena (one cudaMalloc, exported with cudaIpcGetMemHandle):
+//   [mail 4 x kMaxPeerRanks][total 4][barrier flags kMaxPeerRanks] ... padded to kPeerHeaderBytes ... [z0][z1]
 constexpr size_t kPeerMailBytes = 4 * kMaxPeerRanks * sizeof(PeerMail);
-constexpr size_t kPeerHeaderBytes = 1024; // the mailbox, padded
-static_assert(kPeerMailBytes <= kPeerHeaderBytes, "arena header");
+constexpr size_t kPeerBarrierOff = kPeerMailBytes + 4 * sizeof(PeerMail); // arrival counters of the stream-level barrier (mps_comm.cu)
+constexpr size_t kPeerHeaderBytes = 1024;
+static_assert(kPeerBarrierOff + kMaxPeerRanks * sizeof(unsigned long long) <= kPeerHeaderBytes, "arena header");
 struct PeerLink
 {
 	int rank, nranks;
 	unsigned long long tag;          // solve number << 32: flags of earlier solves never match
 	double2* nb_z0[2];               // [0] left, [1] right neighbour's z0 (peer-mapped), nullptr at the ends of the chain
 	double2* nb_z1[2];
-	uint64_t exp_b[2], exp_e[2];     // own rows [b, e) that the left / right neighbour's windows reach (empty if b >= e)
 	PeerMail* mail[kMaxPeerRanks];   // every rank's mailbox (peer-mapped; mail[rank] is local)
 };
 

@@ -67,11 +67,18 @@ struct CgBuffers
 	int stages = 0;          // shared-memory pipeline depth of the streaming kernel
 	int consumer_warps = 8;  // consumer warps per CTA of the streaming kernel (+ 1 producer warp)
 	int lanes_per_row = 1;   // 1 (2-D: ~21 entries per row) or 4 (3-D: ~57)
-	DevBuf<uint32_t> blk_chunks, blk_bytes, blk_cost, chunk_of_row;
-	DevBuf<uint64_t> chunk_base, blob_base, cost_base;
+	DevBuf<uint32_t> blk_chunks, blk_bytes, blk_cost, blk_live, chunk_of_row;
+	DevBuf<uint64_t> chunk_base, blob_base, cost_base, live_base;
 	DevBuf<ChunkDesc> desc;
+	DevBuf<ChunkDesc> live;  // the descriptors of the chunks that have entries, in order (runs of Dummy / Disabled rows and, on several
+	                         // GPUs, the other ranks' rows are not in it): what the CG kernel's CTAs split and walk
 	DevBuf<unsigned char> blobs;
 	uint64_t desc_cap = 0;
+	// load balance of the streaming kernel's CTAs, learnt from the kernel's own cycle counters (mps_cg.cu k_cg_rebalance):
+	DevBuf<double> cta_frac;         // [grid + 1] cumulative share of the modelled cost that CTAs 0..b-1 take (uniform at first)
+	DevBuf<double> cta_speed;        // [grid] smoothed relative speed (modelled cost per cycle) of each CTA
+	DevBuf<unsigned long long> cta_meas; // [2 x grid] {modelled cost taken, SpMV cycles} of the last solve
+	bool adaptive = true;            // MPS_CG_ADAPTIVE=0 freezes the uniform split (bit-reproducible run to run)
 	DevBuf<CgStepScalars> step;      // multi-GPU stepwise solve: scalars of the recurrence on the device ...
 	CgStepScalars* h_step = nullptr; // ... and their pinned host mirror (convergence test)
 	DevBuf<unsigned long long> prof; // per-CTA cycle counters of the last streaming solve (mps_get_cg_profile)
@@ -98,6 +105,13 @@ struct Comm
 	unsigned char* peer_arena[8] = {}; // peers' arenas mapped into this process ([rank] = arena)
 	void* peer_base[8] = {};           // what cudaIpcOpenMemHandle returned (to close)
 	unsigned long long solves = 0;     // persistent solves so far (tag of the mailbox flags)
+	// the replicated particle state over peer memory: pos[2], vel[2], prs[2], nden[2] of every rank mapped here, so that the
+	// per-stage all-gathers are one copy kernel over NVLink between two flag barriers (no NCCL in the step)
+	const void* exported[8] = {};      // the local pointers the current exports refer to (a re-allocation forces a new exchange)
+	unsigned char* peer_state[8][8] = {}; // [rank][2 * field + buffer]
+	void* peer_state_base[8][8] = {};
+	unsigned long long bar_seq = 0;    // stream-level barriers so far (monotonic flag value)
+	uint64_t peer_gathers = 0;
 	PeerLink link{};                   // what the next solve's kernel gets
 };
 } // namespace mps

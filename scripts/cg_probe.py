@@ -28,6 +28,8 @@ if it:
 raw = gpu.cg_profile_raw().astype(float)
 if len(raw) and it:
     import numpy as np
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save(f"gpurun_out/cg_profile_{name}.npy", raw / it)
     for k, nm in enumerate(["phase1", "wait_data", "phase2", "barriers", "producer_wait", "chunks"]):
         v = raw[:, k] / it
         print(f"{nm:14s} min {v.min():10.0f}  p10 {np.percentile(v,10):10.0f}  median {np.median(v):10.0f}  p90 {np.percentile(v,90):10.0f}  max {v.max():10.0f}")

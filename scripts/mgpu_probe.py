@@ -39,6 +39,14 @@ if g.comm_info()["mode"] == "peer-memory" and it:
     for k, nm in enumerate(["phase1", "wait_data", "phase2", "reductions", "producer_wait", "chunks", "iteration"]):
         v = raw[:, k] / (it + (1 if nm in ("wait_data", "producer_wait", "chunks") else 0))
         out[nm] = {"min": float(v.min()), "median": float(np.median(v)), "max": float(v.max()), "cta0": float(v[0])}
+# per-stage device time (adds a sync per stage): where the non-CG part of a multi-GPU step goes, rank by rank
+g.set_cg_profile(False)
+g.set_stage_timing(True)
+g.reset_stats()
+dist.barrier()
+g.forward(2)
+st2 = g.stats_dict()
+out["stage_ms_per_step"] = {k: round(v / 2, 3) for k, v in st2["stage_ms"].items()}
 for r in range(world):
     if r == rank:
         print("PROBE " + json.dumps(out), flush=True)

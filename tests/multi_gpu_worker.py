@@ -21,7 +21,9 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "dambreak2d"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     sc = {"dambreak2d": lambda: scenes.dambreak2d_fast(1.6e-3), "dambreak3d": lambda: scenes.dambreak3d(1.2e-2),
-          "static": lambda: scenes.static_pressure()}[which]()
+          "static": lambda: scenes.static_pressure(),
+          # larger blocks for 4 / 8 ranks (a slab must stay thicker than the neighbour stencil)
+          "dambreak2d_72k": lambda: scenes.dambreak2d_fast(8e-4), "dambreak3d_123k": lambda: scenes.dambreak3d(8e-3)}[which]()
     uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
     if rank == 0:
         uid.copy_(torch.tensor(list(capi.GpuComputer.comm_unique_id()), dtype=torch.uint8))

@@ -69,48 +69,99 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md clocks line).  In-process NVML
+    (pynvml) polled by a thread every 100 ms; falls back to an `nvidia-smi -lms` child process if pynvml is unusable.
+    Samples taken before mark() (warm-up) are dropped."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    MASKS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.rows = []        # (sm_mhz, max_mhz, [reasons])
         self.proc = None
+        self.nvml = None
+        self.t_begin = None   # host time at which the timed region starts: earlier samples are dropped
+        self.stop_flag = False
+        self.how = None
+
+    def mark(self):
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.handle, self.how = pynvml, h, "pynvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                if self.t_begin is not None and time.perf_counter() >= self.t_begin:
+                    self.rows.append((float(sm), float(mx), [nm for nm, m in self.MASKS if bits & m]))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return None
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            if self.t_begin is None or time.perf_counter() < self.t_begin:
+                continue
+            c = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.rows.append((float(c[0]), float(c[1]), [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7])
+                                                             if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def stop(self):
+        time.sleep(0.15)
+        self.stop_flag = True
+        if self.nvml is not None:
+            self.thread.join(timeout=2)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if not self.rows:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({r for row in self.rows for r in row[2]})
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)), "reasons": reasons,
+                "samples": len(self.rows), "how": self.how}
 
 
 def dist_info():
@@ -228,18 +279,26 @@ def main():
         dist.broadcast(uid, 0)
         gpu.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
 
+    # clocks / throttle reasons of rank 0's GPU, sampled DURING the timed region.  The poller is started before the warm-up:
+    # initialising NVML touches every GPU of the box and stalls running CUDA work for tens of milliseconds — invisible
+    # behind one long kernel, but the multi-GPU step runs in lockstep with host syncs.  One poller (rank 0) only.
+    sampler = None
+    if rank == 0:
+        try:
+            uuid = torch.cuda.get_device_properties(local).uuid
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local, uuid)
+        sampler.start()
     # ---- warm-up (untimed), then exactly K steps timed on the device ----
     gpu.forward(args.warmup)
     # both timed legs start from this state (the CG iteration count depends on the state: same state, same work)
     snap = gpu.state()
     snap_t = gpu.time()
     gpu.reset_stats()
-    # clocks / throttle reasons of rank 0's GPU during the timed region (one nvidia-smi poller: the ranks run in lockstep, and a
-    # poller per rank stalls every GPU in turn)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.mark()
     dev_ms = gpu.run_steps(args.steps)
     barrier()
     clocks = sampler.stop() if sampler else None

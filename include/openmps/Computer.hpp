@@ -465,6 +465,25 @@ namespace { namespace OpenMps
 			ForwardTime(dt);
 		}
 
+		// ---- not in the reference ----
+		// The driver's inner loop `while (T() < tNext) ForwardTime();` (Main.cpp:370-376) as one call: DetermineDt, the step and
+		// the time comparison stay on the device side of the C ABI (mps_run_until).  The wall callables are evaluated once, so
+		// this is for walls that do not move during the interval (the reference driver's walls never do, Main.cpp:304-315).
+		// Returns the number of ForwardTime() steps taken.
+		std::size_t RunUntil(const double tNext)
+		{
+			if (!(environment.T() < tNext)) return 0;
+			PushWallPositions();
+			particlesStale = true;
+			std::uint64_t steps = 0;
+			const int rc = mps_run_until(device.h, tNext, &steps);
+			double t = 0, dt = 0;
+			if (mps_get_time(device.h, &t, &dt) == MPS_OK) { environment.Dt() = dt; environment.SetT(t); }
+			typesStale = true; // particles may have left the grid during the interval
+			Check(rc);
+			return static_cast<std::size_t>(steps);
+		}
+
 		// append particles (reference :1754-1777)
 		template<typename PARTICLES>
 		void AddParticles(PARTICLES&& src)

@@ -115,6 +115,7 @@ namespace { namespace OpenMps
 		double N0() const { return n0; }
 
 		// ---- not in the reference: what mps_create needs ----
+		void SetT(const double value) { t = value; } // after a device-resident run of several steps (Computer::RunUntil)
 		double ArgMaxDt() const { return argMaxDt; }
 		double ArgCourant() const { return argCourant; }
 		double ArgG() const { return argG; }

@@ -254,3 +254,56 @@ def lattice(dim, num, l0, r_e_by_l0, margin_cells=2.0, courant=0.1, g=9.8, max_d
     lo = tuple([-margin_cells * l0 * num] * dim); hi = tuple([margin_cells * l0 * num] * dim)
     env = Env(dim, max_dt, courant, g, 998.2, 1.004e-6, r_e_by_l0, l0, lo, hi, eps)
     return Scene(env, x, np.zeros_like(x), np.zeros(len(t)), np.zeros(len(t)), t, f"lattice{dim}d_{num}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def write_xml(scene, path, start_time=0.0, end_time=1.0, output_interval=5e-3, min_step_count_per_output=None, pretty=True):
+    """The run description the reference's driver reads (Main.cpp:186-274), in the layout its generators write
+    (Benchmark/DamBreak/generate_koshizukaoka1996.py:47-149: `value` attributes, particle table as CSV text with
+    ``str(float)`` numbers).  ``max_dt`` of the scene becomes outputInterval / minStepCountPerOutput."""
+    import xml.etree.ElementTree as ET
+    from xml.dom import minidom
+
+    env = scene.env
+    if min_step_count_per_output is None:
+        min_step_count_per_output = max(1, int(round(output_interval / env.max_dt)))
+    root = ET.Element("openmps")
+    c = ET.SubElement(root, "condition")
+    for key, v in (("startTime", start_time), ("endTime", end_time), ("outputInterval", output_interval), ("eps", env.eps)):
+        ET.SubElement(c, key).set("value", str(v))
+    e = ET.SubElement(root, "environment")
+    for key, v in (("l_0", env.l0), ("minStepCountPerOutput", int(min_step_count_per_output)), ("courant", env.courant), ("g", env.g),
+                   ("rho", env.rho), ("nu", env.nu), ("r_eByl_0", env.r_e_by_l0), ("surfaceRatio", 0.97)):
+        ET.SubElement(e, key).set("value", str(v))
+    axes = ("X", "Z") if env.dim == 2 else ("X", "Y", "Z")
+    for k, ax in enumerate(axes):
+        ET.SubElement(e, "min" + ax).set("value", str(float(env.min_x[k])))
+    for k, ax in enumerate(axes):
+        ET.SubElement(e, "max" + ax).set("value", str(float(env.max_x[k])))
+    cols = "Type, x, z, u, w, p, n\n" if env.dim == 2 else "Type, x, y, z, u, v, w, p, n\n"
+    rows = [cols]
+    d = env.dim
+    for i in range(scene.count):
+        vals = [str(int(scene.type[i]))] + [repr(float(v)) for v in scene.x[i]] + [repr(float(v)) for v in scene.u[i]] + \
+               [repr(float(scene.p[i])), repr(float(scene.n[i]))]
+        rows.append(", ".join(vals) + "\n")
+    p = ET.SubElement(root, "particles")
+    p.set("type", "csv")
+    p.text = "".join(rows)
+    text = minidom.parseString(ET.tostring(root)).toprettyxml(indent="\t") if pretty else ET.tostring(root, encoding="unicode")
+    with open(path, "w") as f:
+        f.write(text)
+    return path
+
+
+def read_result_csv(path):
+    """result/particles_%05d.csv (Main.cpp:31-67) -> dict of arrays."""
+    with open(path) as f:
+        header = [h.strip() for h in f.readline().split(",")]
+        data = np.loadtxt(f, delimiter=",", ndmin=2)
+    dim = 3 if "y" in header else 2
+    col = {h: k for k, h in enumerate(header)}
+    xs = ["x", "z"] if dim == 2 else ["x", "y", "z"]
+    us = ["u", "w"] if dim == 2 else ["u", "v", "w"]
+    return {"type": data[:, col["Type"]].astype(np.int32), "x": data[:, [col[a] for a in xs]], "u": data[:, [col[a] for a in us]],
+            "p": data[:, col["p"]], "n": data[:, col["n"]]}

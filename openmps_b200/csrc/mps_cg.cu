@@ -959,6 +959,7 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 		if ((e = cudaMemcpyAsync(c.cta_speed.p, one.data(), one.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) return e;
 		if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return e; // the host vectors go out of scope
 		if (const char* v = std::getenv("MPS_CG_ADAPTIVE")) c.adaptive = std::atoi(v) != 0;
+		if (L.grid > 256) c.adaptive = false; // k_cg_rebalance is one block of 256 threads, one per CTA
 	}
 	CgStreamArgs& a = L.a;
 	a.n = c.n; a.desc = c.live.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);

@@ -35,9 +35,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NPROC = os.cpu_count() or 1
-# the CPU arms use every host core (OpenMP inside the reference); must be set before the libraries are loaded
-os.environ.setdefault("OMP_NUM_THREADS", str(NPROC))
-os.environ.setdefault("OMP_PROC_BIND", "close")
+
+
+def configure_openmp(argv, environ):
+    """OpenMP settings of the CPU arms; must run before any library that brings libgomp is loaded.
+
+    * `--impl reference`: the reference's CPU code uses every host core, also under torchrun (which exports
+      OMP_NUM_THREADS=1 to its workers; only rank 0 computes in this arm), threads bound close.
+    * our arm on one GPU: the same settings, for the `cpu_baseline` leg that runs in this process.
+    * our arm on several GPUs: nothing is touched.  OMP_PROC_BIND makes libgomp bind the INITIAL thread of every process
+      that loads it to the first core of the (shared) affinity mask: all ranks' host threads would time-share one core, and the
+      lockstep multi-GPU step waits for the slowest host (measured: 69 instead of 51 ms/step on 4 GPUs)."""
+    is_reference = any(a == "reference" and i > 0 and argv[i - 1] == "--impl" for i, a in enumerate(argv)) or "--impl=reference" in argv
+    world = int(environ.get("WORLD_SIZE", "1"))
+    if is_reference:
+        environ["OMP_NUM_THREADS"] = str(NPROC)
+        environ.setdefault("OMP_PROC_BIND", "close")
+    elif world == 1:
+        environ.setdefault("OMP_NUM_THREADS", str(NPROC))
+        environ.setdefault("OMP_PROC_BIND", "close")
+    return is_reference, world
+
+
+configure_openmp(sys.argv, os.environ)
 
 import numpy as np  # noqa: E402
 
@@ -70,7 +90,7 @@ def read_peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md clocks line).  In-process NVML
-    (pynvml) polled by a thread every 100 ms; falls back to an `nvidia-smi -lms` child process if pynvml is unusable.
+    (pynvml) polled by a thread every 250 ms; falls back to an `nvidia-smi -lms` child process if pynvml is unusable.
     Samples taken before mark() (warm-up) are dropped."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -109,7 +129,7 @@ class ClockSampler:
             self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.how = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -129,7 +149,7 @@ class ClockSampler:
                     self.rows.append((float(sm), float(mx), [nm for nm, m in self.MASKS if bits & m]))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.25)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -184,7 +204,7 @@ def reference_arm(args, rank, world):
         sc = WORKLOADS[name][0]()
     eng = bind.RefComputer.from_scene(sc, fast=True) if use_ref else bind.PortComputer.from_scene(sc)
     kind = "reference" if use_ref else "port"
-    cores = NPROC if use_ref else 1
+    cores = min(NPROC, int(os.environ.get("OMP_NUM_THREADS", NPROC))) if use_ref else 1
     t_start = time.perf_counter()
     warm = 0
     while warm < args.warmup and time.perf_counter() - t_start < REFERENCE_BUDGET_S / 3:
@@ -216,7 +236,8 @@ def cpu_baseline_one_step(sc, name):
     from oracle import bind
     use_ref = bind.available(sc.env.dim, sc.env.central_gravity, fast=True)
     if use_ref:
-        eng = bind.RefComputer.from_scene(sc, fast=True); kind = "reference"; cores = NPROC
+        eng = bind.RefComputer.from_scene(sc, fast=True); kind = "reference"
+        cores = min(NPROC, int(os.environ.get("OMP_NUM_THREADS", NPROC)))
         steps = 1 if sc.count > 300000 else (5 if sc.count > 30000 else 50)
     else:
         # the scalar restatement is too slow for a 1M step: bounded sub-sample instead

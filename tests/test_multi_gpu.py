@@ -97,3 +97,26 @@ def test_two_gpus_match_one_gpu(scene, steps, coupling):
     assert r0["err_x"] <= 1e-9 and r0["err_u"] <= 1e-6 and r0["err_n"] <= 1e-9 and r0["err_p"] <= 1e-5, r0
     assert abs(r0["iters"] - r0["iters_1gpu"]) <= max(3, 0.01 * r0["iters_1gpu"]), r0
     assert r0["comm_calls"] and r0["comm_calls"] > 0
+
+
+def test_bench_leaves_openmp_binding_alone_on_several_gpus():
+    """bench.py must not export OMP_PROC_BIND to multi-GPU ranks (libgomp would bind every rank's host thread to the same
+    core), must give the CPU reference arm every core even under torchrun, and keeps the one-GPU settings for cpu_baseline."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    env_before = dict(os.environ)
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        nproc = str(mod.NPROC)
+        e = {"WORLD_SIZE": "4", "OMP_NUM_THREADS": "1"}
+        assert mod.configure_openmp(["bench.py", "--gpus", "4"], e) == (False, 4)
+        assert e == {"WORLD_SIZE": "4", "OMP_NUM_THREADS": "1"}
+        e = {"WORLD_SIZE": "4", "OMP_NUM_THREADS": "1"}
+        assert mod.configure_openmp(["bench.py", "--impl", "reference", "--gpus", "4"], e) == (True, 4)
+        assert e["OMP_NUM_THREADS"] == nproc and e["OMP_PROC_BIND"] == "close"
+        e = {}
+        assert mod.configure_openmp(["bench.py"], e) == (False, 1)
+        assert e == {"OMP_NUM_THREADS": nproc, "OMP_PROC_BIND": "close"}
+    finally:
+        os.environ.clear(); os.environ.update(env_before)

@@ -28,15 +28,11 @@
 
 namespace { namespace OpenMps
 {
+	// number of space dimensions and the index of each axis in a Vector (z is always the last: gravity points along -z)
 #ifdef DIM3
-	static constexpr std::size_t DIM = 3;
-	static constexpr std::size_t AXIS_X = 0;
-	static constexpr std::size_t AXIS_Y = 1;
-	static constexpr std::size_t AXIS_Z = 2;
+	static constexpr std::size_t DIM{ 3 }, AXIS_X{ 0 }, AXIS_Y{ 1 }, AXIS_Z{ 2 };
 #else
-	static constexpr std::size_t DIM = 2;
-	static constexpr std::size_t AXIS_X = 0;
-	static constexpr std::size_t AXIS_Z = 1;
+	static constexpr std::size_t DIM{ 2 }, AXIS_X{ 0 }, AXIS_Z{ 1 };
 #endif
 }}
 

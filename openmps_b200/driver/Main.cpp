@@ -123,8 +123,8 @@ namespace
 		auto&& particles = io::LoadParticles(*xml);
 		std::printf("condition: eps=%.17g startTime=%.17g endTime=%.17g outputInterval=%.17g\n", condition.Eps, condition.StartTime, condition.EndTime,
 			condition.OutputInterval);
-		std::printf("environment: dim=%zu l_0=%.17g MaxDt=%.17g MaxDx=%.17g R_e=%.17g Rho=%.17g Nu=%.17g NeighborLength=%.17g\n", OpenMps::DIM,
-			environment.L_0, environment.MaxDt, environment.MaxDx, environment.R_e, environment.Rho, environment.Nu, environment.NeighborLength);
+		std::printf("environment: dim=%zu l_0=%.17g MaxDt=%.17g MaxDx=%.17g R_e=%.17g Rho=%.17g Nu=%.17g NeighborLength=%.17g n0=%.17g\n", OpenMps::DIM,
+			environment.L_0, environment.MaxDt, environment.MaxDx, environment.R_e, environment.Rho, environment.Nu, environment.NeighborLength, environment.N0());
 		const auto offset = static_cast<std::size_t>(std::ceil(condition.StartTime / condition.OutputInterval));
 		const auto count = io::OutputToCsv(particles, offset, directory);
 		std::cout << "wrote " << io::CsvFileName(offset, directory) << ", " << count << " particles not disabled" << std::endl;

@@ -56,6 +56,11 @@ def test_xml_in_csv_out_round_trip(tmp_path, which):
     assert float(kv["l_0"]) == sc.env.l0
     assert float(kv["MaxDx"]) == sc.env.courant * sc.env.l0
     assert float(kv["R_e"]) == sc.env.r_e_by_l0 * sc.env.l0
+    # derived constants of the host-side Environment against the reference build / its CPU restatement, bit for bit
+    from oracle import bind
+    ref = (bind.RefComputer if bind.available(sc.env.dim, sc.env.central_gravity) else bind.PortComputer).from_scene(sc).env_values()
+    for ours, theirs in (("n0", "n0"), ("MaxDx", "MaxDx"), ("R_e", "R_e"), ("NeighborLength", "NeighborLength")):
+        assert float(kv[ours]) == ref[theirs], (ours, kv[ours], ref[theirs])
     # and what comes back is what went in, to the 6 significant digits of the format
     back = scenes.read_result_csv(str(out / "particles_00002.csv"))
     assert np.array_equal(back["type"], sc.type)

@@ -89,12 +89,6 @@ def main():
     # symmetric Gauss-Seidel (SSOR, omega = 1): two triangular solves = sequential on a GPU; listed as the quality yard-stick
     L = sp.tril(A, 0).tocsr(); U = sp.triu(A, 0).tocsr()
     run("SSOR(1) [sequential solves]", lambda r: spla.spsolve_triangular(U, d * spla.spsolve_triangular(L, r, lower=True), lower=False), 2.0)
-    # incomplete Cholesky-like: ILU(0) of the SPD matrix
-    try:
-        ilu = spla.spilu(A.tocsc(), drop_tol=0.0, fill_factor=1.0)
-        run("ILU(0) [sequential solves]", ilu.solve, 2.0)
-    except Exception as ex:
-        print("  ILU(0) failed:", ex)
     # Chebyshev polynomial in D^-1 A of degree k: k extra SpMVs per iteration, no dot products, fully parallel
     Dinv = sp.diags(1.0 / d)
     lam_max = spla.eigsh(Dinv @ A, k=1, which="LM", return_eigenvectors=False, tol=1e-3)[0] * 1.05

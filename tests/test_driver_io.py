@@ -169,3 +169,65 @@ def test_reads_the_reference_sample_xml(tmp_path):
     cond = next(l for l in r.stdout.splitlines() if l.startswith("condition:"))
     kv = dict(t.split("=") for t in cond.split()[1:])
     assert (float(kv["eps"]), float(kv["startTime"]), float(kv["endTime"]), float(kv["outputInterval"])) == (1e-10, 0.0, 1.0, 0.005)
+
+
+def _model_input_from_csv(text):
+    """Python restatement of InputFromCsv (Main.cpp:70-183): split at '\\n', leading zero-length lines skipped, blanks and tabs
+    removed from every line, header names decide the columns, empty lines skipped."""
+    lines = text.split("\n")
+    k = 0
+    while lines[k] == "":
+        k += 1
+
+    def items(line):
+        s = line.replace(" ", "").replace("\t", "")
+        return s.split(",") if s else []
+    names = ["Type", "x", "z", "u", "w", "p", "n"]
+    head = items(lines[k]); k += 1
+    for h in head:
+        if h not in names:
+            raise ValueError("Illegal header item in input csv")
+    if any(nm not in head for nm in names):
+        raise ValueError("Some header item doesn't exist")
+    col = {nm: head.index(nm) if head.count(nm) == 1 else max(i for i, h in enumerate(head) if h == nm) for nm in names}
+    rows = []
+    for line in lines[k:]:
+        d = items(line)
+        if d:
+            rows.append((int(d[col["Type"]]), float(d[col["x"]]), float(d[col["z"]]), float(d[col["u"]]), float(d[col["w"]]), float(d[col["p"]]), float(d[col["n"]])))
+    return rows
+
+
+def test_csv_parser_against_a_model_of_the_reference_parser(tmp_path):
+    rng = np.random.default_rng(20261017)
+    names = ["Type", "x", "z", "u", "w", "p", "n"]
+
+    def pad(tok):
+        ws = ["", " ", "  ", "\t", " \t"]
+        return ws[rng.integers(len(ws))] + tok + ws[rng.integers(len(ws))]
+
+    def number():
+        kind = rng.integers(5)
+        v = [rng.normal(), rng.normal() * 1e-9, rng.normal() * 1e7, float(rng.integers(-5, 6)), 0.0][kind]
+        return [repr(float(v)), "%g" % v, "%.3e" % v, "%d" % int(v) if float(v).is_integer() else "%r" % float(v)][rng.integers(4)]
+    for case in range(12):
+        order = list(rng.permutation(names))
+        lines = [""] * int(rng.integers(0, 3))
+        lines.append(",".join(pad(h) for h in order))
+        for _ in range(int(rng.integers(1, 40))):
+            if rng.random() < 0.15:
+                lines.append(["", "   ", "\t"][rng.integers(3)])          # empty lines anywhere after the header
+                continue
+            vals = {nm: number() for nm in names}
+            vals["Type"] = str(int(rng.integers(0, 4)))
+            lines.append(",".join(pad(vals[h]) for h in order))
+        body = "\n".join(lines) + "\n"
+        want = _model_input_from_csv(body)
+        d = tmp_path / f"c{case}"
+        d.mkdir()
+        r = _check(d, _xml(body))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"{len(want)} particles" in r.stdout
+        got = (d / "result" / "particles_00000.csv").read_text().splitlines()[1:]
+        exp = [", ".join([str(t)] + ["%g" % v for v in rest]) for (t, *rest) in want]
+        assert got == exp, case

@@ -1,7 +1,7 @@
 """Physical observables of the reference's benchmarks as functions of a particle state.
 
 The reference computes them in plotting scripts that read result/particles_%05d.csv; here the same definitions work on a state
-dict ({"type", "x", "u", "p", "n"}, as returned by GpuComputer.state(), the oracle, or scenes.read_result_csv) so that
+dict ({"type", "x", "u", "p", "n"}, as returned by GpuComputer.state(), a CPU checker, or scenes.read_result_csv) so that
 long-run physical agreement is an assertion, not a figure:
 
 * ``dam_break_edge``            Benchmark/DamBreak/koshizukaoka1996_edge.py:14-20, :55-63

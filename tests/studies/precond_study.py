@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """CPU study for SURVEY.md 8f rank 2 (preconditioned CG): which preconditioner would cut the CG iterations of the MPS pressure
-Poisson equation, and by how much, on matrices taken from the CPU restatement of the reference (test infrastructure only).
+Poisson equation, and by how much, on matrices taken from the CPU restatement of the reference.  It lives under tests/ because it uses the oracle, which only
+tests, smoke() and the CPU arms of bench.py may touch.
 
 For one developed state of a dam break: the system A x = b of the step (active rows only), solved with the reference's stopping
 rule (||r||^2 < ||r0||^2 eps^2, warm start from the previous pressure) by plain CG and by PCG with candidate preconditioners.
 Reported: iterations, and the number of matrix-sized memory sweeps per iteration each one costs on the GPU (the CG kernel is
 bound by matrix bytes), i.e. the bound on the speed-up a streaming implementation could reach.
 
-usage: tools/precond_study.py [l0=1.6e-3] [steps=40]
+usage: tests/studies/precond_study.py [l0=1.6e-3] [steps=40]
 """
 import os
 import sys
@@ -17,7 +18,7 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from openmps_b200 import scenes  # noqa: E402
 from oracle import bind  # noqa: E402

@@ -12,4 +12,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_cg_stream -s 3 -c 1 -o gpurun_out/prof_cg \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_cg.log 2>&1
+# FP64 pipe peak (the roofline denominator of the gather kernels)
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu && tools/fp64_peak > gpurun_out/fp64_peak.json 2>&1; cat gpurun_out/fp64_peak.json
 ls -la gpurun_out | head -30

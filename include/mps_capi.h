@@ -174,6 +174,13 @@ int mps_set_cg_profile(mps_handle h, int on);
 int mps_get_cg_profile(mps_handle h, double* out /* 19 doubles */);
 int mps_get_cg_profile_raw(mps_handle h, uint64_t* out /* 8 per CTA */, uint64_t capacity_ctas, uint64_t* ctas);
 
+/* ---- environment variables read by the library (tuning and tests; none is needed in normal use) ---------------------------
+ *   MPS_CG_ADAPTIVE=0      freeze the CG kernel's CTA split (uniform): runs become bit-identical; default: re-balanced every solve
+ *   MPS_COMM_NCCL_ONLY=1   several GPUs: couple the ranks through NCCL between per-phase launches instead of peer memory
+ *   MPS_CG_WARPS, MPS_CG_LPR, MPS_CG_STAGES, MPS_CG_COST_FIXED   chunk geometry / pipeline depth / load-balance model of k_cg_stream
+ *   MPS_CG_GENERIC=1       solve assembled systems with the generic CSR kernel (k_cg_solve) instead of the streaming one
+ */
+
 #ifdef __cplusplus
 }
 #endif

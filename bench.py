@@ -412,7 +412,11 @@ def main():
                    "parallelism": "1 GPU" if world == 1 else f"{world} x-slabs of the cell-sorted slots, one per GPU (CG coupling: {comm['mode']}; "
                                   f"{st['comm_calls']} NCCL calls in the timed region)",
                    "l2_policy": l2_policy,
-                   "cg_iterations_per_step": iters / max(args.steps, 1)},
+                   "cg_iterations_per_step": iters / max(args.steps, 1),
+                   "matrix_sweeps_per_step": st["matrix_sweeps"] / max(args.steps, 1),
+                   "ppe_solver": (f"CG preconditioned by Jacobi + one multigrid V(1,1) cycle on the cell hierarchy ({st['mg_levels']} levels, "
+                                  f"{st['mg_cells']} cells), reference stopping rule" if st["mg_levels"] else
+                                  "plain CG (the reference's algorithm, Computer.hpp:1359-1429)")},
         "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }

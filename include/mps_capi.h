@@ -79,6 +79,9 @@ typedef struct mps_stats
 	double cg_bytes;           /* algorithmic bytes of those solves: sum of iterations x (12 nnz + 92 active rows), SURVEY 8d */
 	double stage_ms[16];       /* accumulated CUDA-event time per stage when stage timing is on (see mps_stage_name) */
 	uint64_t stage_calls[16];
+	uint64_t matrix_sweeps;    /* passes over the assembled matrix (one per CG iteration + the initial residual), summed since the last reset */
+	uint64_t mg_levels;        /* levels of the cell hierarchy the last solve's preconditioner used (0 = plain CG) */
+	uint64_t mg_cells;         /* occupied cells of the neighbour grid = unknowns of the first coarse level, last step */
 } mps_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------------------------------- */
@@ -175,6 +178,10 @@ int mps_get_cg_profile(mps_handle h, double* out /* 19 doubles */);
 int mps_get_cg_profile_raw(mps_handle h, uint64_t* out /* 8 per CTA */, uint64_t capacity_ctas, uint64_t* ctas);
 
 /* ---- environment variables read by the library (tuning and tests; none is needed in normal use) ---------------------------
+ *   MPS_CG_PRECOND=0       solve the PPE with the reference's plain CG (Computer.hpp:1359-1429) instead of the multigrid-preconditioned
+ *                          CG (default; same system, same stopping rule, ~30x fewer iterations; csrc/mps_mg.cu)
+ *   MPS_MG_OMEGA, MPS_MG_GAMMA, MPS_MG_TOP_SWEEPS, MPS_MG_TOP_CELLS   Jacobi damping (0.8), over-correction (1.8), extra sweeps (4) on
+ *                          the top level and its size limit (64 cells) of the preconditioner's V-cycle
  *   MPS_CG_ADAPTIVE=0      freeze the CG kernel's CTA split (uniform): runs become bit-identical; default: re-balanced every solve
  *   MPS_COMM_NCCL_ONLY=1   several GPUs: couple the ranks through NCCL between per-phase launches instead of peer memory
  *   MPS_CG_WARPS, MPS_CG_LPR, MPS_CG_STAGES, MPS_CG_COST_FIXED   chunk geometry / pipeline depth / load-balance model of k_cg_stream

@@ -35,7 +35,8 @@ class MpsStats(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("cg_iterations", C.c_uint64), ("last_cg_iterations", C.c_uint64),
                 ("last_rr0", C.c_double), ("last_rr", C.c_double),
                 ("particles", C.c_uint64), ("neighbors", C.c_uint64), ("nnz", C.c_uint64), ("active_rows", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("disabled_last", C.c_uint64), ("comm_calls", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16)]
+                ("kernel_launches", C.c_uint64), ("disabled_last", C.c_uint64), ("comm_calls", C.c_uint64), ("cg_ms", C.c_double), ("cg_bytes", C.c_double), ("stage_ms", C.c_double * 16), ("stage_calls", C.c_uint64 * 16),
+                ("matrix_sweeps", C.c_uint64), ("mg_levels", C.c_uint64), ("mg_cells", C.c_uint64)]
 
 
 class MpsError(RuntimeError):
@@ -328,6 +329,7 @@ class GpuComputer:
         return {"steps": st.steps, "cg_iterations": st.cg_iterations, "last_cg_iterations": st.last_cg_iterations,
                 "last_rr0": st.last_rr0, "last_rr": st.last_rr, "particles": st.particles, "neighbors": st.neighbors,
                 "nnz": st.nnz, "active_rows": st.active_rows, "kernel_launches": st.kernel_launches, "comm_calls": st.comm_calls, "disabled_last": st.disabled_last, "cg_ms": st.cg_ms, "cg_bytes": st.cg_bytes,
+                "matrix_sweeps": st.matrix_sweeps, "mg_levels": st.mg_levels, "mg_cells": st.mg_cells,
                 "stage_ms": {nm: st.stage_ms[i] for i, nm in enumerate(names)},
                 "stage_calls": {nm: st.stage_calls[i] for i, nm in enumerate(names)}}
 
@@ -368,7 +370,7 @@ class GpuComputer:
         """Cycle counters of the last streaming CG solve (see mps_get_cg_profile)."""
         out = (C.c_double * 19)()
         self._check(self.lib.mps_get_cg_profile(self.h, out))
-        names = ["phase1", "wait_data", "phase2", "barriers", "wait_stage", "chunks_per_cta", "iteration_cycles_total", "_"]
+        names = ["phase1", "wait_data", "phase2", "barriers", "wait_stage", "chunks_per_cta", "iteration_cycles_total", "vcycle"]
         d = {"mean": dict(zip(names, out[0:8])), "max": dict(zip(names, out[8:16])), "chunks": out[16], "blob_bytes": out[17], "ctas": out[18]}
         return d
 

@@ -50,6 +50,16 @@ int device_status(mps_solver* s)
 	return fail(s, e, "device error");
 }
 
+int clear_device_error(mps_solver* s);
+
+// The reference's exceptions are per call (a caller may catch one and carry on), so the device flag is cleared once reported.
+int report_device_status(mps_solver* s)
+{
+	const int rc = device_status(s);
+	if (rc != MPS_OK) clear_device_error(s);
+	return rc;
+}
+
 int sync_scalars(mps_solver* s)
 {
 	CU(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, s->stream));
@@ -60,6 +70,7 @@ int clear_device_error(mps_solver* s)
 {
 	CU(cudaMemsetAsync(&s->d_sc->error, 0, sizeof(int), s->stream));
 	s->h_sc->error = 0;
+	s->sort_error = 0;
 	return MPS_OK;
 }
 
@@ -117,6 +128,12 @@ int set_dt_device(mps_solver* s, double dt, int advance, bool from_max_u)
 int step_body(mps_solver* s)
 {
 	{ StageTimer t(s, kStSearch); CU(launch_sort_and_search(s)); }
+	if (s->sort_error == MPS_CELL_OVERFLOW)
+	{
+		// Grid::Store throws out of SearchNeighbor (Grid.hpp:311-318, Computer.hpp:705-717): nothing after the sort runs
+		s->h_sc->error = MPS_CELL_OVERFLOW;
+		return report_device_status(s);
+	}
 	{ StageTimer t(s, kStDensity); CU(launch_density(s, false)); }
 	{ StageTimer t(s, kStEcs); CU(launch_ecs(s)); }
 	{ StageTimer t(s, kStExplicit); CU(launch_explicit(s)); }
@@ -153,8 +170,11 @@ int finish_step(mps_solver* s)
 		if (cudaEventElapsedTime(&ms, s->ev_cg0, s->ev_cg1) == cudaSuccess) s->stats.cg_ms += ms;
 		s->stats.cg_bytes += static_cast<double>(s->h_sc->cg_iterations) *
 			(12.0 * static_cast<double>(s->h_sc->nnz_total) + 92.0 * static_cast<double>(s->h_sc->active_rows));
+		s->stats.matrix_sweeps += s->h_sc->cg_iterations + 1; // one SpMV per iteration + the initial residual
 	}
-	return device_status(s);
+	s->stats.mg_levels = mg_active(s) ? s->h_sc->mg_levels : 0;
+	s->stats.mg_cells = mg_active(s) ? s->mg.cells0 : 0;
+	return report_device_status(s);
 }
 
 } // namespace
@@ -246,6 +266,7 @@ int mps_create(const mps_env* env, double eps, int device, mps_handle* out)
 	if ((e = cudaMemsetAsync(s->d_sc, 0, sizeof(DevScalars), s->stream)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaMemset");
 	if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaStreamSynchronize");
 	if ((e = cg_configure(s)) != cudaSuccess) return cuda_fail(nullptr, e, "cg_configure");
+	mg_configure(s);
 	*out = sp.release();
 	return MPS_OK;
 }
@@ -272,6 +293,13 @@ int mps_destroy(mps_handle s)
 	s->cg.blk_chunks.release(); s->cg.blk_bytes.release(); s->cg.chunk_of_row.release(); s->cg.chunk_base.release();
 	s->cg.blob_base.release(); s->cg.blk_cost.release(); s->cg.cost_base.release(); s->cg.cta_frac.release(); s->cg.cta_speed.release(); s->cg.cta_meas.release(); s->cg.desc.release(); s->cg.live.release(); s->cg.blk_live.release(); s->cg.live_base.release(); s->cg.blobs.release(); s->cg.prof.release();
 	s->stage_d.release(); s->stage_i.release(); s->flush.release();
+	for (int l = 0; l < kMgMaxLevels; l++)
+	{
+		MgLevelBufs& b = s->mg.lv[l];
+		b.flag.release(); b.rank.release(); b.key.release(); b.nbr.release(); b.child.release(); b.parent.release();
+		b.S.release(); b.dinv.release(); b.r.release(); b.e0.release(); b.e1.release();
+	}
+	s->mg.crow.release(); s->mg.cstart.release(); s->mg.dinv0.release(); s->mg.row_s.release();
 	if (s->d_sc) cudaFree(s->d_sc);
 	if (s->h_sc) cudaFreeHost(s->h_sc);
 	if (s->ev0) cudaEventDestroy(s->ev0);
@@ -482,7 +510,7 @@ int mps_search_neighbor(mps_handle s)
 	{ StageTimer t(s, kStSearch); CU(launch_sort_and_search(s)); }
 	int rc = sync_scalars(s); if (rc) return rc;
 	s->stats.disabled_last = s->h_sc->disabled_now;
-	return device_status(s);
+	return report_device_status(s);
 }
 int mps_compute_density(mps_handle s) { STAGE_PROLOGUE; STAGE_NEEDS_SEARCH; StageTimer t(s, kStDensity); CU(launch_density(s, false)); return MPS_OK; }
 int mps_error_correction(mps_handle s) { STAGE_PROLOGUE; STAGE_NEEDS_SEARCH; StageTimer t(s, kStEcs); CU(launch_ecs(s)); return MPS_OK; }
@@ -504,9 +532,10 @@ int mps_solve_ppe(mps_handle s)
 	s->stats.last_cg_iterations = s->h_sc->cg_iterations;
 	s->stats.cg_iterations += s->h_sc->cg_iterations;
 	s->stats.last_rr0 = s->h_sc->rr0; s->stats.last_rr = s->h_sc->rr;
-	rc = device_status(s);
-	if (rc == MPS_CG_NOT_CONVERGED) clear_device_error(s); // a C++ caller may catch the exception and carry on
-	return rc;
+	s->stats.matrix_sweeps += s->h_sc->cg_iterations + 1;
+	s->stats.mg_levels = mg_active(s) ? s->h_sc->mg_levels : 0;
+	s->stats.mg_cells = mg_active(s) ? s->mg.cells0 : 0;
+	return report_device_status(s); // a C++ caller may catch the exception and carry on
 }
 int mps_assign_pressure(mps_handle s) { STAGE_PROLOGUE; StageTimer t(s, kStPressure); CU(launch_assign_pressure(s)); return MPS_OK; }
 int mps_pressure_gradient(mps_handle s) { STAGE_PROLOGUE; STAGE_NEEDS_SEARCH; StageTimer t(s, kStGradient); CU(launch_gradient(s)); return MPS_OK; }

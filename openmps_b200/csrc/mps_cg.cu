@@ -223,6 +223,7 @@ struct CgStreamArgs
 	double2* z0;               // {r_i, p_i} interleaved, ping-pong pair: ONE window copy per range brings both gathered vectors
 	double2* z1;
 	double* ap;
+	double* r;                 // preconditioned solve only (k_pcg_stream): the residual; z0 / z1 then hold {z, p} with z = M^-1 r
 	double* partials;          // [2][gridDim.x]
 	DevScalars* sc;
 	double eps;
@@ -438,7 +439,7 @@ struct StreamSmem
 // One SpMV phase over this CTA's chunks.  ITER = false: r = b - A x, p_prev = 0 (window of x; result into zcur).
 // ITER = true: p = r + beta p_prev, Ap = A p (window of zprev = {r, p_prev}; p into zcur[].y).
 // Returns this thread's share of r.r / p.Ap.  `it` counts the ring uses so far.
-template<int LPR, bool ITER, bool MG>
+template<int LPR, bool ITER, bool MG, bool PRE = false>
 __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const StreamSmem& sm, const uint32_t c0, const uint32_t c1, const uint32_t live,
 	uint32_t& it, uint32_t& dseq, const double beta, const double2* __restrict__ zprev, double2* __restrict__ zcur,
 	const uint64_t pol_matrix, const uint64_t pol_vector)
@@ -601,7 +602,8 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 				else
 				{
 					const double ri = a.b[row] - acc;
-					zcur[row] = make_double2(ri, 0.0);
+					if (PRE) { a.r[row] = ri; zcur[row] = make_double2(0.0, 0.0); } // z = M^-1 r is formed by the preconditioner
+					else zcur[row] = make_double2(ri, 0.0);
 					local = fma(ri, ri, local);
 				}
 			}
@@ -695,6 +697,7 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 			for (uint64_t i = ctl64[2] + threadIdx.x; i < ctl64[3]; i += nthreads)
 			{
 				a.z0[i] = make_double2(0.0, 0.0); a.z1[i] = make_double2(0.0, 0.0); a.ap[i] = 0.0;
+				if (a.r) a.r[i] = 0.0;
 			}
 		}
 	}
@@ -811,6 +814,276 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 		a.sc->rr0 = rr0;
 		a.sc->rr = rr;
 		a.sc->cg_converged = converged ? 1 : 0;
+		if (!converged) atomicMax(&a.sc->error, static_cast<int>(MPS_CG_NOT_CONVERGED)); // Computer.hpp:1424-1428
+	}
+}
+
+// =====================================================================================================================
+// k_pcg_stream — the same solve, preconditioned:  M^-1 = D^-1 + P1 V P1^T  (mps_mg.cu describes M and builds its operators).
+//
+// Same system, same warm start, same stopping rule on the same (unpreconditioned) residual norm as the reference
+// (||r||^2 < eps^2 ||r0||^2, at most n iterations, Computer.hpp:1382-1428); what changes is the search direction:
+//   p = z + beta p_prev,  z = M^-1 r,  alpha = r.z / p.Ap,  beta = r'.z' / r.z
+// The SpMV phase is k_cg_stream's, untouched: the interleaved pair it gathers is {z, p_prev} instead of {r, p_prev}.
+// Phase 2 grows two row passes and the V-cycle between them (everything on the cell hierarchy is L2-resident and tiny next
+// to the fine matrix; its cost is the grid barriers, one per level and direction):
+//   2a  x += alpha p ; r -= alpha Ap ; r.r ; z0 = r / diag ; level-0 residual = per-cell sums of r (warp-segmented sums over
+//       cell-aligned row ranges: fixed order, no atomics) and its first Jacobi sweep
+//       -> barrier (r.r: the reference's convergence test)
+//   V   down: residual of level l restricted to level l+1 (thread per coarse cell, gather over its 2^D children) + Jacobi
+//       from zero; top: a few more sweeps; up: over-corrected prolongation fused with the post-smoothing sweep
+//   2b  z = z0 + e0[cell(row)] ; r.z  -> barrier
+template<bool FIRST>
+__device__ __forceinline__ double pcg_rows_a(const CgStreamArgs& a, const MgArgs& m, const uint64_t rb, const uint64_t re, const double alpha, double2* __restrict__ zt)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const double* __restrict__ dinv_c = m.lv[0].dinv;
+	double* __restrict__ rc = m.lv[0].r;
+	double* __restrict__ ec = m.lv[0].e0;
+	double local = 0.0, carry = 0.0;
+	uint32_t carry_id = kMgNone;
+	for (uint64_t base = rb; base < re; base += 32) // warp-uniform trip count
+	{
+		const uint64_t i = base + lane;
+		const bool on = i < re;
+		double ri = 0.0;
+		uint32_t id = kMgNone;
+		if (on)
+		{
+			id = __ldg(m.crow + i);
+			if (FIRST) ri = __ldcg(m.r + i);
+			else
+			{
+				const double pi = __ldcg(&zt[i].y), api = __ldcg(a.ap + i);
+				a.x[i] = fma(alpha, pi, __ldcg(a.x + i));
+				ri = fma(-alpha, api, __ldcg(m.r + i));
+				m.r[i] = ri;
+			}
+			zt[i].x = ri * __ldg(m.dinv0 + i);
+			local = fma(ri, ri, local);
+		}
+		// inclusive sums of r inside every run of equal cell ids (ids never decrease along the rows)
+		double v = ri;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const double vu = __shfl_up_sync(0xffffffffu, v, o);
+			const uint32_t iu = __shfl_up_sync(0xffffffffu, id, o);
+			if (lane >= static_cast<unsigned>(o) && iu == id) v += vu;
+		}
+		if (carry_id != kMgNone)
+		{
+			if (id == carry_id) v += carry;                                  // the cell continues from the previous tile
+			else if (lane == 0) { rc[carry_id] = carry; ec[carry_id] = __ldg(dinv_c + carry_id) * carry; } // it ended exactly there
+		}
+		const uint32_t idn = __shfl_down_sync(0xffffffffu, id, 1);
+		const bool tail = on && ((lane == 31) ? (i + 1 == re) : (idn != id));
+		if (tail) { rc[id] = v; ec[id] = __ldg(dinv_c + id) * v; }
+		const double v31 = __shfl_sync(0xffffffffu, v, 31);
+		const uint32_t id31 = __shfl_sync(0xffffffffu, id, 31);
+		const int open31 = __shfl_sync(0xffffffffu, (on && !tail) ? 1 : 0, 31);
+		carry = v31;
+		carry_id = open31 ? id31 : kMgNone;
+	}
+	return local;
+}
+
+__device__ __forceinline__ double pcg_rows_b(const MgArgs& m, const uint64_t rb, const uint64_t re, const double* __restrict__ ef, double2* __restrict__ zt)
+{
+	const unsigned lane = threadIdx.x & 31;
+	double local = 0.0;
+	for (uint64_t i = rb + lane; i < re; i += 32)
+	{
+		const double z = __ldcg(&zt[i].x) + __ldcg(ef + __ldg(m.crow + i));
+		zt[i].x = z;
+		local = fma(__ldcg(m.r + i), z, local);
+	}
+	return local;
+}
+
+// One V(1,1) cycle on the cell hierarchy; on entry lv[0].r and lv[0].e0 = dinv r are complete and visible (the r.r barrier),
+// on return (after a grid barrier) the result is in the returned buffer of level 0.  K = 3^D, CH = 2^D.
+__device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const int L, const int K, const int CH,
+	unsigned long long& bar_target, const unsigned nblocks)
+{
+	const uint64_t gt = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, gs = static_cast<uint64_t>(nblocks) * blockDim.x;
+	const double gamma = m.gamma;
+	// ---- down: r_{l+1} = R (r_l - A_l e_l), e_{l+1} = dinv r_{l+1} ----
+	for (int l = 0; l + 1 < L; l++)
+	{
+		const MgLevelPtrs& lo = m.lv[l];
+		const MgLevelPtrs& hi = m.lv[l + 1];
+		const uint64_t nhi = *hi.count;
+		for (uint64_t C = gt; C < nhi; C += gs)
+		{
+			double sum = 0.0;
+			for (int q = 0; q < CH; q++)
+			{
+				const uint32_t c = __ldg(hi.child + C * CH + q);
+				if (c == kMgNone) continue;
+				double res = __ldcg(lo.r + c);
+				const uint32_t* __restrict__ nb = lo.nbr + static_cast<uint64_t>(c) * K;
+				const double* __restrict__ sv = lo.S + static_cast<uint64_t>(c) * K;
+				for (int s = 0; s < K; s++)
+				{
+					const uint32_t j = __ldg(nb + s);
+					if (j != kMgNone) res = fma(-__ldg(sv + s), __ldcg(lo.e0 + j), res);
+				}
+				sum += res;
+			}
+			hi.r[C] = sum;
+			hi.e0[C] = __ldg(hi.dinv + C) * sum;
+		}
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+	}
+	// ---- top level: more damped-Jacobi sweeps, ping-pong ----
+	const MgLevelPtrs& top = m.lv[L - 1];
+	const uint64_t ntop = *top.count;
+	int cur = 0;
+	for (int t = 0; t < m.top_sweeps; t++)
+	{
+		const double* __restrict__ src = cur ? top.e1 : top.e0;
+		double* __restrict__ dst = cur ? top.e0 : top.e1;
+		for (uint64_t c = gt; c < ntop; c += gs)
+		{
+			double acc = __ldcg(top.r + c);
+			for (int s = 0; s < K; s++)
+			{
+				const uint32_t j = __ldg(top.nbr + c * K + s);
+				if (j != kMgNone) acc = fma(-__ldg(top.S + c * K + s), __ldcg(src + j), acc);
+			}
+			dst[c] = fma(__ldg(top.dinv + c), acc, __ldcg(src + c));
+		}
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		cur ^= 1;
+	}
+	const double* ehi = cur ? top.e1 : top.e0;
+	// ---- up: e_l <- e_l + gamma P e_{l+1}, then one Jacobi sweep; the prolongated neighbours are formed on the fly ----
+	for (int l = L - 2; l >= 0; l--)
+	{
+		const MgLevelPtrs& lv = m.lv[l];
+		const uint64_t nl = *lv.count;
+		for (uint64_t c = gt; c < nl; c += gs)
+		{
+			double acc = __ldcg(lv.r + c);
+			for (int s = 0; s < K; s++)
+			{
+				const uint32_t j = __ldg(lv.nbr + c * K + s);
+				if (j != kMgNone)
+				{
+					const double ej = fma(gamma, __ldcg(ehi + __ldg(lv.parent + j)), __ldcg(lv.e0 + j));
+					acc = fma(-__ldg(lv.S + c * K + s), ej, acc);
+				}
+			}
+			const double ec = fma(gamma, __ldcg(ehi + __ldg(lv.parent + c)), __ldcg(lv.e0 + c));
+			lv.e1[c] = fma(__ldg(lv.dinv + c), acc, ec);
+		}
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		ehi = lv.e1;
+	}
+	return ehi;
+}
+
+template<int LPR>
+__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m, int K, int CH)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const StreamCta cta = stream_setup<true, false>(a, smem_raw);
+	const StreamSmem& sm = cta.sm;
+	double* red = cta.red;
+	const uint32_t c0 = cta.c0, c1 = cta.c1, live = cta.live;
+	const uint64_t pol_matrix = cta.pol_matrix, pol_vector = cta.pol_vector;
+	const uint64_t n = a.n;
+	const unsigned nblocks = gridDim.x;
+	// consecutive reductions must use different partial-sum buffers (a fast CTA may write its next partial while a slow one still
+	// adds up the previous ones); the plain barriers of the V-cycle do not change that, so the buffer simply alternates per reduction
+	unsigned part_sel = 0;
+	auto next_part = [&]() { double* q = a.partials + (part_sel & 1u) * nblocks; part_sel++; return q; };
+	unsigned long long bar_target = 0, seq = 0;
+	uint32_t it = 0, dseq = 0;
+	const bool prof_on = (a.prof != nullptr) && (threadIdx.x == 0);
+	const bool meas_on = (a.cta_meas != nullptr) && (threadIdx.x == 0);
+	unsigned long long spmv_cycles = 0;
+
+	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA)
+	int L = 1;
+	while (L < m.levels && *m.lv[L - 1].count > m.top_cells) L++;
+	// this warp's rows in phase 2: a cell-aligned range, the level-0 cells split evenly over all warps of the grid
+	uint64_t rb, re;
+	{
+		const uint64_t cells = *m.lv[0].count;
+		const uint64_t wpb = blockDim.x >> 5, W = static_cast<uint64_t>(nblocks) * wpb, gw = static_cast<uint64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+		const uint64_t cb = cells / W * gw + cells % W * gw / W, ce = cells / W * (gw + 1) + cells % W * (gw + 1) / W;
+		rb = m.cstart[cb]; re = m.cstart[ce];
+	}
+
+	// ---- r0 = b - A x ; p_prev = 0 ; rr = r0.r0 (Computer.hpp:1382-1386) ----
+	double local = spmv_phase<LPR, false, false, true>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
+	double rr = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+	const double rr0 = rr;
+	const double tol = rr * a.eps * a.eps;     // Computer.hpp:1386
+	bool converged = (tol == 0);                // Computer.hpp:1389
+	double2* zprev = a.z0; // {z, p_prev}
+	double2* zcur = a.z1;  // receives {z', p}
+	double rz = 0.0, beta = 0.0;
+	uint64_t iter = 0;
+	if (!converged)
+	{
+		// z0 = M^-1 r0
+		pcg_rows_a<true>(a, m, rb, re, 0.0, zprev);
+		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		const double* ef = mg_vcycle(a, m, L, K, CH, bar_target, nblocks);
+		local = pcg_rows_b(m, rb, re, ef, zprev);
+		rz = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+	}
+
+	while (iter < n && !converged)
+	{
+		// ---- phase 1: p = z + beta p_prev ; Ap = A p ; p.Ap ----
+		const long long t0 = (prof_on || meas_on) ? clock64() : 0;
+		local = spmv_phase<LPR, true, false>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
+		const long long t1 = (prof_on || meas_on) ? clock64() : 0;
+		spmv_cycles += static_cast<unsigned long long>(t1 - t0);
+		const double pAp = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		const double alpha = rz / pAp;
+
+		// ---- phase 2a: x, r, r.r, Jacobi part of z, level-0 residual ----
+		local = pcg_rows_a<false>(a, m, rb, re, alpha, zcur);
+		const double rr_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		iter++;
+		rr = rr_new;
+		converged = (rr_new < tol);            // Computer.hpp:1407-1408
+		if (converged) break;
+
+		// ---- coarse part of z and r.z ----
+		const long long t2 = prof_on ? clock64() : 0;
+		const double* ef = mg_vcycle(a, m, L, K, CH, bar_target, nblocks);
+		const long long t3 = prof_on ? clock64() : 0;
+		local = pcg_rows_b(m, rb, re, ef, zcur);
+		const double rz_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		if (prof_on)
+		{
+			const long long t4 = clock64();
+			unsigned long long* pr = a.prof + blockIdx.x * 8;
+			pr[0] += static_cast<unsigned long long>(t1 - t0);  // phase 1 (SpMV)
+			pr[2] += static_cast<unsigned long long>((t2 - t1) + (t4 - t3)); // p.Ap reduction, row passes 2a / 2b, their reductions
+			pr[7] += static_cast<unsigned long long>(t3 - t2);  // V-cycle (barriers included)
+			pr[6] += static_cast<unsigned long long>(t4 - t0);
+		}
+		beta = rz_new / rz;
+		rz = rz_new;
+		{ double2* t = zprev; zprev = zcur; zcur = t; } // zprev now holds {z, p} of this iteration
+	}
+
+	if (meas_on) a.cta_meas[nblocks + blockIdx.x] = spmv_cycles;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		a.sc->z_final = (zprev == a.z1) ? 1 : 0;
+		a.sc->cg_iterations = iter;
+		a.sc->rr0 = rr0;
+		a.sc->rr = rr;
+		a.sc->cg_converged = converged ? 1 : 0;
+		a.sc->mg_levels = static_cast<unsigned int>(L);
 		if (!converged) atomicMax(&a.sc->error, static_cast<int>(MPS_CG_NOT_CONVERGED)); // Computer.hpp:1424-1428
 	}
 }
@@ -963,7 +1236,7 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 	}
 	CgStreamArgs& a = L.a;
 	a.n = c.n; a.desc = c.live.p; a.blobs = c.blobs.p; a.b = c.b.p; a.x = c.x.p; a.z0 = reinterpret_cast<double2*>(c.z0.p); a.z1 = reinterpret_cast<double2*>(c.z1.p);
-	a.ap = c.ap.p; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
+	a.ap = c.ap.p; a.r = nullptr; a.partials = c.partials.p; a.sc = s->d_sc; a.eps = s->env.eps;
 	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
 	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
 	a.l2_stream = ((s->nbr_total + (s->own1() - s->own0())) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
@@ -1022,6 +1295,73 @@ cudaError_t launch_stream(mps_solver* s)
 	return cudaGetLastError();
 }
 
+// the preconditioned solve (one GPU): same launch geometry as k_cg_stream + the level tables of mps_mg.cu
+template<int LPR>
+cudaError_t launch_pcg(mps_solver* s)
+{
+	CgBuffers& c = s->cg;
+	MgBuffers& g = s->mg;
+	StreamLaunch L;
+	cudaError_t e = prepare_stream(s, L);
+	if (e != cudaSuccess) return e;
+	L.a.r = c.r.p;
+	MgArgs m{};
+	m.levels = g.levels; m.top_sweeps = g.top_sweeps; m.top_cells = g.top_cells; m.gamma = g.gamma;
+	m.crow = g.crow.p; m.cstart = g.cstart.p; m.dinv0 = g.dinv0.p; m.r = c.r.p;
+	for (int l = 0; l < g.levels; l++)
+	{
+		MgLevelBufs& b = g.lv[l];
+		MgLevelPtrs& q = m.lv[l];
+		q.count = b.rank.p + b.dense; q.S = b.S.p; q.nbr = b.nbr.p; q.dinv = b.dinv.p; q.child = b.child.p; q.parent = b.parent.p;
+		q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p;
+	}
+	int K = (s->env.dim == 3) ? 27 : 9, CH = 1 << s->env.dim;
+	e = cudaFuncSetAttribute(k_pcg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_stream<LPR>, L.threads, L.smem_bytes);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
+	if (e != cudaSuccess) return e;
+	if (s->cg_profile)
+	{
+		e = c.prof.ensure(8ull * L.grid, s->stream);
+		if (e != cudaSuccess) return e;
+		e = cudaMemsetAsync(c.prof.p, 0, 8ull * L.grid * sizeof(unsigned long long), s->stream);
+		if (e != cudaSuccess) return e;
+		L.a.prof = c.prof.p;
+		c.prof_blocks = L.grid;
+	}
+	if (c.adaptive)
+	{
+		e = cudaMemsetAsync(c.cta_meas.p, 0, 2ull * L.grid * sizeof(unsigned long long), s->stream);
+		if (e != cudaSuccess) return e;
+		L.a.cta_meas = c.cta_meas.p;
+	}
+	void* params[] = { &L.a, &m, &K, &CH };
+	s->stats.kernel_launches += 1;
+	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_stream<LPR>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	if (e != cudaSuccess) return e;
+	if (c.adaptive)
+	{
+		k_cg_rebalance<<<1, 256, 0, s->stream>>>(c.cta_meas.p, c.cta_speed.p, c.cta_frac.p, L.grid);
+		s->stats.kernel_launches += 1;
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_pcg_lpr(mps_solver* s)
+{
+	switch (s->cg.lanes_per_row)
+	{
+	case 1: return launch_pcg<1>(s);
+	case 2: return launch_pcg<2>(s);
+	case 4: return launch_pcg<4>(s);
+	default: return launch_pcg<8>(s);
+	}
+}
+
 template<bool MG>
 cudaError_t launch_stream_lpr(mps_solver* s)
 {
@@ -1078,6 +1418,12 @@ cudaError_t launch_lpr(mps_solver* s, CgArgs& args, unsigned want_blocks)
 
 } // namespace
 
+// the preconditioner needs the cell hierarchy of an assembled system; several GPUs still run the plain solve
+bool mg_active(const mps_solver* s)
+{
+	return s->mg.on && s->cg.chunked && !s->cg.external && !s->comm.on;
+}
+
 cudaError_t launch_cg(mps_solver* s)
 {
 	CgBuffers& c = s->cg;
@@ -1088,6 +1434,7 @@ cudaError_t launch_cg(mps_solver* s)
 	}
 	// multi-GPU: the persistent kernel coupled through peer memory when the ranks could map each other's arenas, else NCCL stepwise
 	if (c.chunked && !c.external && s->comm.on) return (s->comm.peer_mode == 1) ? launch_stream_lpr<true>(s) : comm_cg_solve(s);
+	if (mg_active(s)) return launch_pcg_lpr(s);
 	if (c.chunked && !c.external) return launch_stream_lpr<false>(s);
 	CgArgs args;
 	args.n = c.n; args.rowptr = c.rowptr.p; args.col = c.col.p; args.val = c.val.p; args.b = c.b.p;

@@ -556,6 +556,7 @@ int mps_comm_init(mps_handle s, int rank, int nranks, const void* id128)
 	const ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
 	if (r != ncclSuccess) { s->last_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return MPS_NCCL_ERROR; }
 	s->comm.nccl = comm; s->comm.rank = rank; s->comm.nranks = nranks; s->comm.on = true;
+	s->mg.on = false; // the cell hierarchy of the preconditioner is single-GPU for now: several ranks run the plain solve
 	return MPS_OK;
 }
 

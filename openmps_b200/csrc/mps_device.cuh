@@ -64,6 +64,9 @@ struct DevScalars
 	unsigned long long blob_total;  // bytes of all chunk blobs of the last assembly
 	unsigned long long cost_total;  // sum of the chunk cost model (load balance of the CG kernel)
 	unsigned long long grid_barrier; // arrival counter of the CG kernel's grid barrier (zeroed before each launch)
+	unsigned int mg_levels;         // levels of the cell hierarchy the last preconditioned solve used (0: plain CG)
+	unsigned int pad0_;
+	unsigned long long mg_cells0;   // occupied cells of the neighbour grid at the last sort
 };
 
 // ---- PPE in "chunk blob" form (what the CG kernel streams, DESIGN.md "CG kernel") ---------------------------------------
@@ -132,6 +135,34 @@ struct PeerLink
 	double2* nb_z0[2];               // [0] left, [1] right neighbour's z0 (peer-mapped), nullptr at the ends of the chain
 	double2* nb_z1[2];
 	PeerMail* mail[kMaxPeerRanks];   // every rank's mailbox (peer-mapped; mail[rank] is local)
+};
+
+// ---- multigrid preconditioner on the cell hierarchy (mps_mg.cu builds it, mps_cg.cu k_pcg_stream applies it) --------------
+constexpr uint32_t kMgNone = 0xffffffffu;
+constexpr int kMgMaxLevels = 16;
+struct MgLevelPtrs
+{
+	const uint64_t* count;   // occupied cells of this level (device value: the total of the level's rank scan)
+	const double* S;         // [cells][3^D] Galerkin stencil, centre at 3^D / 2
+	const uint32_t* nbr;     // [cells][3^D] compact id of the neighbour cell or kMgNone
+	const double* dinv;      // [cells] omega / centre entry (0 where the centre is 0)
+	const uint32_t* child;   // [cells][2^D] compact ids one level down (levels >= 1)
+	const uint32_t* parent;  // [cells] compact id one level up (all but the last level)
+	double* r;               // [cells] restricted residual
+	double* e0;              // [cells] correction, two buffers (Jacobi sweeps ping-pong)
+	double* e1;
+};
+struct MgArgs
+{
+	int levels;              // levels built (the kernel stops at the first one with <= top_cells cells)
+	int top_sweeps;          // extra damped-Jacobi sweeps on the top level
+	uint32_t top_cells;
+	double gamma;            // over-correction of every coarse-grid correction
+	const uint32_t* crow;    // [rows] level-0 cell of a row (kMgNone for Disabled rows)
+	const uint64_t* cstart;  // [cells0 + 1] first row of every level-0 cell; last entry = rows that lie in cells
+	const double* dinv0;     // [rows] 1 / a_ii (0 for rows without entries)
+	double* r;               // [rows] residual
+	MgLevelPtrs lv[kMgMaxLevels];
 };
 
 template<int D>

@@ -312,17 +312,38 @@ struct PpeOut
 	const ChunkDesc* desc; const uint32_t* chunk_of_row; unsigned char* blobs;           // chunk blobs
 };
 
-template<int D, bool CHUNKED>
-__global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
-	const double* __restrict__ ecs, PpeOut out, double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
+// PRE = true additionally leaves behind what the multigrid preconditioner is built from (mps_mg.cu): 1 / a_ii, and the row's
+// entries summed per cell of the 3^D stencil around the row's own cell (the cell of a slot is the one the sort put it in, so
+// every neighbour of the list lies in that stencil): row_s[s * stride + i].
+struct PpePre
 {
+	const uint32_t* skey; double* row_s; double* dinv0; uint64_t stride;
+};
+
+template<int D, bool CHUNKED, bool PRE>
+__global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t n, Particles<D> P, Lists L, const double* __restrict__ nws,
+	const double* __restrict__ ecs, PpeOut out, PpePre pre, double* __restrict__ b, double* __restrict__ x, EnvConst env, DevScalars* sc)
+{
+	constexpr int K = (D == 3) ? 27 : 9;
+	__shared__ double sacc[PRE ? K : 1][kThreads]; // [slot][thread]: conflict-free, dynamically indexed by slot
 	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const uint8_t t = P.type[i];
 	if ((t == kDummy) || (t == kDisabled))
 	{
 		b[i] = 0; x[i] = 0;
+		if (PRE) pre.dinv0[i] = 0;
 		return;
+	}
+	// slot of cell(j) in the stencil of cell(i): keys are x-major ... z-minor, so key_j - key_i + (all offsets + 1) is the
+	// mixed-radix number (dx + 1, [dy + 1,] dz + 1) in radices (., [ny,] nz); every axis has >= 3 cells (Grid.hpp:140-150: +2 spare)
+	const int nzc = static_cast<int>(env.grid_n[D - 1]), nyc = (D == 3) ? static_cast<int>(env.grid_n[1]) : 1;
+	const long long key_i = PRE ? static_cast<long long>(pre.skey[i]) : 0;
+	const int key_shift = (D == 3) ? (nyc * nzc + nzc + 1) : (nzc + 1);
+	if (PRE)
+	{
+#pragma unroll
+		for (int s = 0; s < K; s++) sacc[s][threadIdx.x] = 0.0;
 	}
 	atomicAdd(&sc->active_rows, 1ull); // same address for the whole warp: aggregated by the compiler into one atomic
 	const double dt = sc->dt;
@@ -381,6 +402,12 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 			return 0.0;
 		});
 	put(static_cast<uint32_t>(i), a_ii);
+	if (PRE)
+	{
+		pre.dinv0[i] = (a_ii != 0) ? 1.0 / a_ii : 0.0;
+#pragma unroll
+		for (int s = 0; s < K; s++) pre.row_s[static_cast<uint64_t>(s) * pre.stride + i] = sacc[s][threadIdx.x];
+	}
 }
 
 // multi-rank only: right-hand side 0 and initial guess x = P (Computer.hpp:1195-1220) for EVERY row; the owners then
@@ -699,6 +726,8 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 	// the streaming kernel stages even-aligned windows: one element of slack behind every vector
 	MPS_TRY(cg.b.ensure(n + 64, st)); MPS_TRY(cg.x.ensure(n + 64, st)); if (!cg.chunked) MPS_TRY(cg.r.ensure(n + 64, st));
 	MPS_TRY(cg.ap.ensure(n + 64, st));
+	const bool pre_on = s->mg.on && cg.chunked && !s->comm.on; // == mg_active(s) once cg.external is reset below
+	if (pre_on) MPS_TRY(cg.r.ensure(n + 64, st));
 	if (cg.chunked && s->comm.on) MPS_TRY(comm_ensure_arena(s, n + 64)); // {r, p} live in the arena the neighbour ranks map
 	else if (cg.chunked) { MPS_TRY(cg.z0.ensure(2 * (n + 64), st)); MPS_TRY(cg.z1.ensure(2 * (n + 64), st)); }
 	else { MPS_TRY(cg.p0.ensure(n + 64, st)); MPS_TRY(cg.p1.ensure(n + 64, st)); }
@@ -723,15 +752,20 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 		k_ppe_guess<D><<<blocks_for(n, kThreads), kThreads, 0, st>>>(n, view<D>(s), cg.b.p, cg.x.p);
 		s->stats.kernel_launches += 1;
 	}
+	PpePre pre{};
+	if (pre_on) { pre.skey = s->skey.p; pre.row_s = s->mg.row_s.p; pre.dinv0 = s->mg.dinv0.p; pre.stride = n; }
 	if (nb)
 	{
-		if (cg.chunked)
-			k_ppe_fill<D, true><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
+		if (cg.chunked && pre_on)
+			k_ppe_fill<D, true, true><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, pre, cg.b.p, cg.x.p, s->env, s->d_sc);
+		else if (cg.chunked)
+			k_ppe_fill<D, true, false><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, pre, cg.b.p, cg.x.p, s->env, s->d_sc);
 		else
-			k_ppe_fill<D, false><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, cg.b.p, cg.x.p, s->env, s->d_sc);
+			k_ppe_fill<D, false, false><<<nb, kThreads, 0, st>>>(r0, r1, view<D>(s), lists(s), s->nws.p, s->ecs.p, out, pre, cg.b.p, cg.x.p, s->env, s->d_sc);
 		s->stats.kernel_launches += 1;
 	}
 	MPS_TRY(cudaMemcpyAsync(&s->d_sc->nnz_total, cg.rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+	if (pre_on) MPS_TRY(launch_mg_setup(s)); // topology + Galerkin operators of the cell hierarchy for this assembly
 	return cudaGetLastError();
 }
 template<int D> cudaError_t assign_pressure(mps_solver* s)

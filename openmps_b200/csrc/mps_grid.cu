@@ -249,6 +249,8 @@ cudaError_t sort_and_search(mps_solver* s)
 	k_cell_key<D><<<nb, kThreads, 0, st>>>(n, cur.pos, cur.type, s->key.p, s->rank.p, s->cell_count.p, env, s->d_sc);
 	// 2. cell start table (entry ncells = start of the Disabled tail, entry ncells + 1 = n)
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->cell_count.p, s->cell_start.p, env.ncells + 1, s->scan_tmp, st, &s->stats.kernel_launches));
+	// 2b. occupied cells -> compact ids: level 0 of the multigrid preconditioner's cell hierarchy (mps_mg.cu)
+	MPS_TRY(launch_mg_rank0(s));
 	// 3. scatter, deterministic order inside each cell, permute the state
 	k_scatter<<<nb, kThreads, 0, st>>>(n, s->key.p, s->rank.p, s->cell_start.p, cur.orig, s->perm.p, s->perm_orig.p);
 	k_rank_fix<<<nb, kThreads, 0, st>>>(n, static_cast<uint32_t>(env.ncells), s->key.p, s->cell_start.p, s->perm.p, s->perm_orig.p, s->perm2.p);
@@ -265,10 +267,19 @@ cudaError_t sort_and_search(mps_solver* s)
 	if (nbo) k_search<D, false><<<nbo, kThreads, 0, st>>>(r0, r1, pos, s->skey.p, s->cell_start.p, s->nbr_cnt.p, nullptr, nullptr, env);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->nbr_cnt.p, s->nbr_ptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
-	// the list length is needed on the host to size the buffer: one 8-byte read-back per step
-	uint64_t total = 0;
+	// the list length is needed on the host to size the buffer: the step's one host round trip.  The same read brings the
+	// number of occupied cells (sizes the preconditioner's levels) and the device error flag: a step whose sort overflowed a
+	// cell stops HERE, like the reference's Grid::Exception thrown from Store (Grid.hpp:311-318), before any later stage could
+	// run on over-full cells.
+	uint64_t total = 0, cells0 = 0;
+	int dev_error = 0;
 	MPS_TRY(cudaMemcpyAsync(&total, s->nbr_ptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	if (s->mg.on) MPS_TRY(cudaMemcpyAsync(&cells0, s->mg.lv[0].rank.p + s->mg.lv[0].dense, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	MPS_TRY(cudaMemcpyAsync(&dev_error, &s->d_sc->error, sizeof(int), cudaMemcpyDeviceToHost, st));
 	MPS_TRY(cudaStreamSynchronize(st));
+	s->sort_error = dev_error;
+	if (dev_error == MPS_CELL_OVERFLOW) { s->nbr_total = 0; s->searched = false; return cudaSuccess; }
+	MPS_TRY(mg_ensure(s, cells0));
 	MPS_TRY(s->nbr.ensure(total + 1, st));
 	if (nbo) k_search<D, true><<<nbo, kThreads, 0, st>>>(r0, r1, pos, s->skey.p, s->cell_start.p, nullptr, s->nbr_ptr.p, s->nbr.p, env);
 	s->stats.kernel_launches += 1;

@@ -85,6 +85,31 @@ struct CgBuffers
 	unsigned prof_blocks = 0;
 };
 
+// multigrid preconditioner of the PPE solve: per-level device buffers (mps_mg.cu)
+struct MgLevelBufs
+{
+	long long dims[3] = { 1, 1, 1 }; // dense grid of the level
+	uint64_t dense = 0;              // product of dims
+	uint64_t bound = 0;              // upper bound of the occupied cells (sizes the compact arrays and the launches)
+	DevBuf<uint32_t> flag;           // [dense] occupied?
+	DevBuf<uint64_t> rank;           // [dense + 1] exclusive scan of flag = compact id; last entry = occupied cells
+	DevBuf<uint32_t> key, nbr, child, parent;
+	DevBuf<double> S, dinv, r, e0, e1;
+};
+struct MgBuffers
+{
+	bool on = false;                 // MPS_CG_PRECOND (default on): assembled systems are solved by k_pcg_stream
+	int levels = 0;
+	double omega = 0.8, gamma = 1.8;
+	int top_sweeps = 4;
+	uint32_t top_cells = 64;
+	uint64_t cells0 = 0;             // occupied cells of the neighbour grid at the last sort (read back with the list size)
+	MgLevelBufs lv[kMgMaxLevels];
+	DevBuf<uint32_t> crow;
+	DevBuf<uint64_t> cstart;
+	DevBuf<double> dinv0, row_s;
+};
+
 } // namespace mps
 
 namespace mps {
@@ -151,10 +176,12 @@ struct mps_solver
 	mps::DevBuf<uint32_t> nbr;
 	uint64_t nbr_total = 0;
 	bool searched = false;
+	int sort_error = 0;      // device error flag as read back with the list size (MPS_CELL_OVERFLOW stops the step there)
 
 	// PPE
 	mps::DevBuf<uint32_t> row_len;
 	mps::CgBuffers cg;
+	mps::MgBuffers mg;
 	uint64_t nnz_total = 0;
 
 	// staging for upload / download (original order)
@@ -219,6 +246,12 @@ cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /
 	uint64_t* launches);
 // mps_chunk.cu
 cudaError_t launch_chunk_build(mps_solver* s);          // row_len, skey, cell_start -> chunk descriptors + row offsets
+// mps_mg.cu
+void mg_configure(mps_solver* s);                       // level geometry from the grid extents, MPS_CG_PRECOND / MPS_MG_* switches
+cudaError_t launch_mg_rank0(mps_solver* s);             // during the sort: occupied cells -> compact ids
+cudaError_t mg_ensure(mps_solver* s, uint64_t cells0);  // sizes every level for `cells0` occupied cells
+cudaError_t launch_mg_setup(mps_solver* s);             // after k_ppe_fill: topology + Galerkin operators of every level
+bool mg_active(const mps_solver* s);                    // this solve is preconditioned (single GPU, chunked, switch on)
 // mps_cg.cu
 cudaError_t cg_configure(mps_solver* s);                // picks chunk limits / pipeline depth for this environment
 cudaError_t launch_cg(mps_solver* s);

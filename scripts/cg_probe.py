@@ -22,8 +22,10 @@ print(json.dumps({"workload": name, "n": sc.count, "ms_per_step": ms / 2, "cg_ms
                   "us_per_iter": 1e3 * st["cg_ms"] / max(st["cg_iterations"], 1), "nnz": st["nnz"], "profile": pr}, indent=1))
 m = pr["mean"]
 if it:
-    print("per iteration (cycles, mean over CTAs): phase1 %.0f  wait_data %.0f  phase2 %.0f  barriers %.0f  producer_wait %.0f  chunks/CTA %.1f  total %.0f" % (
-        m["phase1"] / it, m["wait_data"] / (it + 1), m["phase2"] / it, m["barriers"] / it, m["wait_stage"] / (it + 1), m["chunks_per_cta"] / (it + 1), m["iteration_cycles_total"] / it))
+    print("per iteration (cycles, mean over CTAs): phase1 %.0f  wait_data %.0f  phase2 %.0f  barriers %.0f  producer_wait %.0f  chunks/CTA %.1f  vcycle %.0f  total %.0f" % (
+        m["phase1"] / it, m["wait_data"] / (it + 1), m["phase2"] / it, m["barriers"] / it, m["wait_stage"] / (it + 1), m["chunks_per_cta"] / (it + 1), m["vcycle"] / it,
+        m["iteration_cycles_total"] / it))
+    print("preconditioner: levels %d, cells %d, matrix sweeps %d" % (st["mg_levels"], st["mg_cells"], st["matrix_sweeps"]))
 
 raw = gpu.cg_profile_raw().astype(float)
 if len(raw) and it:

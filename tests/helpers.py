@@ -65,7 +65,16 @@ class StepReport(dict):
     """stage -> metric values collected while replaying a golden step (kept for printing on failure)."""
 
 
-def replay_golden_step(eng, g, exact, resync=True, tol=1e-12, cg_tol=1e-6):
+def check_iterations(got, want, plain_cg):
+    """plain CG (the reference's algorithm, MPS_CG_PRECOND=0) must take the reference's iteration count to within 10 %;
+    the preconditioned solve must not need more than that."""
+    if plain_cg:
+        assert abs(got - want) <= max(3, want // 10), (got, want)
+    else:
+        assert got <= want + 3, (got, want)
+
+
+def replay_golden_step(eng, g, exact, resync=True, tol=1e-12, cg_tol=1e-6, plain_cg=True):
     """Replays the recorded reference step stage by stage on ``eng`` and asserts parity after every stage.
 
     exact=True  : floating-point outputs must be bit-identical (CPU restatement vs reference).
@@ -132,7 +141,7 @@ def replay_golden_step(eng, g, exact, resync=True, tol=1e-12, cg_tol=1e-6):
         eps = float(g["env_eps"])
         rep["cg_residual_ratio"] = float(np.dot(r, r) / max(np.dot(r0, r0), 1e-300))
         assert np.dot(r, r) <= 4.0 * eps * eps * np.dot(r0, r0) + 1e-300, "true residual outside the stopping tolerance"
-        assert abs(eng.last_iterations() - int(g["cg_iterations"])) <= max(3, int(g["cg_iterations"]) // 10), rep["cg_iterations"]
+        check_iterations(eng.last_iterations(), int(g["cg_iterations"]), plain_cg)
     if exact:
         eng.stage("implicit")
     else:

@@ -143,6 +143,12 @@ int mps_get_vec(mps_handle h, int which, double* out);
 /* load an arbitrary CSR system into ppe.{A,b,x} (the CG known-answer tests, test_ComputerConjugateGradient.cpp:93-107) */
 int mps_set_system(mps_handle h, uint64_t n, const uint64_t* rowptr, const uint32_t* col, const double* val, const double* b, const double* x0);
 int mps_get_solution(mps_handle h, uint64_t n, double* x);
+/* The multigrid preconditioner of the PPE solve (no counterpart in the reference, whose CG is unpreconditioned): tables of the
+ * cell hierarchy after the last assembly, for the tests that check them against P^T A P.  level >= 0: which = 0 cell key (u32),
+ * 1 neighbour ids (u32 x 3^D), 2 children (u32 x 2^D), 3 parent (u32), 4 Galerkin stencil (f64 x 3^D), 5 omega / centre,
+ * 6 r, 7 e0, 8 e1 (f64); level = -1: 0 row -> cell (u32 x n), 1 first row of every cell (u64 x cells + 1), 2 1 / a_ii (f64 x n),
+ * 3 slot -> original particle id (u32 x n).  *count = elements available; at most capacity_bytes are copied to out. */
+int mps_debug_mg(mps_handle h, int level, int which, void* out, uint64_t capacity_bytes, uint64_t* count);
 
 /* ---- multi-GPU (no counterpart in the reference, which is single-process OpenMP) ------------------------------------
  * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,

@@ -107,6 +107,7 @@ def load_library():
     sig("mps_comm_info", [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64)])
     sig("mps_comm_mode", [vp, C.POINTER(C.c_int)])
     sig("mps_partition_range", [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)])
+    sig("mps_debug_mg", [vp, C.c_int, C.c_int, vp, u64, C.POINTER(u64)])
     sig("mps_set_cg_profile", [vp, C.c_int])
     sig("mps_get_cg_profile", [vp, pd])
     sig("mps_get_cg_profile_raw", [vp, vp, u64, C.POINTER(u64)])
@@ -307,6 +308,19 @@ class GpuComputer:
 
     def last_iterations(self):
         return int(self.stats().last_cg_iterations)
+
+    def mg_table(self, level, which):
+        """One table of the preconditioner's cell hierarchy (see mps_debug_mg)."""
+        n = C.c_uint64(0)
+        self._check(self.lib.mps_debug_mg(self.h, level, which, None, 0, C.byref(n)))
+        if level < 0:
+            dt = {0: np.uint32, 1: np.uint64, 2: np.float64, 3: np.uint32}[which]
+        else:
+            dt = np.uint32 if which <= 3 else np.float64
+        out = np.zeros(n.value, dtype=dt)
+        if n.value:
+            self._check(self.lib.mps_debug_mg(self.h, level, which, _ptr(out), out.nbytes, C.byref(n)))
+        return out
 
     # ---- measurement ----
     def set_stage_timing(self, on):

@@ -741,6 +741,56 @@ int mps_get_solution(mps_handle s, uint64_t n, double* x)
 	return MPS_OK;
 }
 
+// Tables of the multigrid preconditioner after the last assembly (tests/test_multigrid.py checks them against P^T A P computed
+// on the host).  level >= 0: which = 0 key (u32), 1 nbr (u32 x 3^D), 2 child (u32 x 2^D), 3 parent (u32), 4 S (f64 x 3^D), 5 dinv, 6 r,
+// 7 e0, 8 e1 (f64); level = -1: which = 0 row -> cell (u32 x n), 1 first row of every cell (u64 x cells + 1), 2 1 / a_ii (f64 x n),
+// 3 slot -> original id (u32 x n).  *count = elements available; at most capacity_bytes are copied.
+int mps_debug_mg(mps_handle s, int level, int which, void* out, uint64_t capacity_bytes, uint64_t* count)
+{
+	STAGE_PROLOGUE; NEED(count);
+	if (!mg_active(s)) return fail(s, MPS_BAD_ARG, "no preconditioner on this handle");
+	const MgBuffers& g = s->mg;
+	const uint64_t K = (s->env.dim == 3) ? 27 : 9, CH = 1ull << s->env.dim;
+	const void* src = nullptr; uint64_t elems = 0, esize = 8;
+	if (level < 0)
+	{
+		switch (which)
+		{
+		case 0: src = g.crow.p; elems = s->n; esize = 4; break;
+		case 1: src = g.cstart.p; elems = g.cells0 + 1; esize = 8; break;
+		case 2: src = g.dinv0.p; elems = s->n; esize = 8; break;
+		case 3: src = s->orig[s->cur].p; elems = s->n; esize = 4; break;
+		default: return fail(s, MPS_BAD_ARG, "bad table id");
+		}
+	}
+	else
+	{
+		if (level >= g.levels) return fail(s, MPS_BAD_ARG, "no such level");
+		const MgLevelBufs& b = g.lv[level];
+		uint64_t cells = 0;
+		CU(cudaMemcpyAsync(&cells, b.rank.p + b.dense, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+		CU(cudaStreamSynchronize(s->stream));
+		switch (which)
+		{
+		case 0: src = b.key.p; elems = cells; esize = 4; break;
+		case 1: src = b.nbr.p; elems = cells * K; esize = 4; break;
+		case 2: src = b.child.p; elems = level > 0 ? cells * CH : 0; esize = 4; break;
+		case 3: src = b.parent.p; elems = (level + 1 < g.levels) ? cells : 0; esize = 4; break;
+		case 4: src = b.S.p; elems = cells * K; break;
+		case 5: src = b.dinv.p; elems = cells; break;
+		case 6: src = b.r.p; elems = cells; break;
+		case 7: src = b.e0.p; elems = cells; break;
+		case 8: src = b.e1.p; elems = cells; break;
+		default: return fail(s, MPS_BAD_ARG, "bad table id");
+		}
+	}
+	*count = elems;
+	const uint64_t bytes = std::min<uint64_t>(elems * esize, capacity_bytes);
+	if (out && bytes && src) CU(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return MPS_OK;
+}
+
 // ---- measurement -----------------------------------------------------------------------------------------------------
 int mps_set_stage_timing(mps_handle s, int on) { NEED(s); s->stage_timing = on != 0; return MPS_OK; }
 int mps_get_stats(mps_handle s, mps_stats* out)

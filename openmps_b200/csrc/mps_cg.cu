@@ -745,6 +745,10 @@ template<int LPR, bool MG>
 __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// An earlier stage of this step failed (cell overflow, a chunk that does not fit the stages): the descriptors may not be
+	// trustworthy, so no CTA touches them.  Every CTA reads the flag before its first barrier, and the only writer inside this
+	// kernel is the very end of the solve: the decision is the same everywhere.
+	if (*reinterpret_cast<volatile int*>(&a.sc->error) != 0) return;
 	const StreamCta cta = stream_setup<true, MG>(a, smem_raw);
 	const StreamSmem& sm = cta.sm;
 	double* red = cta.red;
@@ -988,6 +992,7 @@ template<int LPR>
 __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m, int K, int CH)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
+	if (*reinterpret_cast<volatile int*>(&a.sc->error) != 0) return; // see k_cg_stream
 	const StreamCta cta = stream_setup<true, false>(a, smem_raw);
 	const StreamSmem& sm = cta.sm;
 	double* red = cta.red;

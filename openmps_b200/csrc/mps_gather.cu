@@ -385,6 +385,13 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 		else col[w] = j;
 		val[w] = a;
 		w++;
+		if (PRE)
+		{
+			const int m = static_cast<int>(static_cast<long long>(pre.skey[j]) - key_i + key_shift);
+			const int dz1 = m % nzc, rest = m / nzc;
+			const int slot = (D == 3) ? ((rest / nyc) * 3 + (rest % nyc)) * 3 + dz1 : rest * 3 + dz1;
+			sacc[slot][threadIdx.x] += a;
+		}
 	};
 
 	// matrix row, Computer.hpp:1246-1327

@@ -182,6 +182,10 @@ int mps_flush_l2(mps_handle h);                   /* writes a buffer larger than
 int mps_set_cg_profile(mps_handle h, int on);
 int mps_get_cg_profile(mps_handle h, double* out /* 19 doubles */);
 int mps_get_cg_profile_raw(mps_handle h, uint64_t* out /* 8 per CTA */, uint64_t capacity_ctas, uint64_t* ctas);
+/* preconditioned solve, cycles summed over the last solve as CTA 0 sees them: [l] restriction to level l + 1 (barrier included),
+ * [16] top-level sweeps, [17] wait for the hand-back barrier, [20 + l] prolongation + smoothing of level l, [40] row pass 2a,
+ * [41] row pass 2b, [42] r.r reduction, [43] p.Ap reduction, [44] r.z reduction */
+int mps_get_cg_profile_stages(mps_handle h, uint64_t* out /* 64 */);
 
 /* ---- environment variables read by the library (tuning and tests; none is needed in normal use) ---------------------------
  *   MPS_CG_PRECOND=0       solve the PPE with the reference's plain CG (Computer.hpp:1359-1429) instead of the multigrid-preconditioned

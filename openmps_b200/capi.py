@@ -111,6 +111,7 @@ def load_library():
     sig("mps_set_cg_profile", [vp, C.c_int])
     sig("mps_get_cg_profile", [vp, pd])
     sig("mps_get_cg_profile_raw", [vp, vp, u64, C.POINTER(u64)])
+    sig("mps_get_cg_profile_stages", [vp, vp])
     _lib = lib
     return lib
 
@@ -387,6 +388,11 @@ class GpuComputer:
         names = ["phase1", "wait_data", "phase2", "barriers", "wait_stage", "chunks_per_cta", "iteration_cycles_total", "vcycle"]
         d = {"mean": dict(zip(names, out[0:8])), "max": dict(zip(names, out[8:16])), "chunks": out[16], "blob_bytes": out[17], "ctas": out[18]}
         return d
+
+    def cg_profile_stages(self):
+        out = np.zeros(64, dtype=np.uint64)
+        self._check(self.lib.mps_get_cg_profile_stages(self.h, _ptr(out)))
+        return out
 
     def cg_profile_raw(self):
         out = np.zeros((1024, 8), dtype=np.uint64)

@@ -837,6 +837,16 @@ int mps_get_cg_profile_raw(mps_handle s, uint64_t* out, uint64_t capacity_ctas, 
 	return MPS_OK;
 }
 
+int mps_get_cg_profile_stages(mps_handle s, uint64_t* out)
+{
+	STAGE_PROLOGUE; NEED(out);
+	for (int k = 0; k < 64; k++) out[k] = 0;
+	if (!s->cg.prof_stages || !s->cg.prof.p || !s->cg.prof_blocks) return MPS_OK;
+	CU(cudaMemcpyAsync(out, s->cg.prof.p + 8ull * s->cg.prof_blocks, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return MPS_OK;
+}
+
 int mps_flush_l2(mps_handle s)
 {
 	STAGE_PROLOGUE;

@@ -238,7 +238,9 @@ struct CgStreamArgs
 	PeerLink peer;             // multi-GPU persistent solve (k_cg_stream<LPR, true>): neighbours' buffers and mailboxes over NVLink
 };
 
+constexpr int kProfStages = 64;     // per-stage counters of the preconditioned solve behind the per-CTA ones (CgBuffers::prof)
 constexpr int kMaxStreamWarps = 17;
+constexpr int kStreamWarps2d = 9;   // 2-D: at most 8 consumer warps + 1 producer warp
 constexpr unsigned kGroups = 2; // consumer groups working on alternate chunks
 constexpr uint32_t kDescBatch = 16; // descriptors per half of the producer's descriptor ring
 
@@ -837,6 +839,8 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_cg_stream(CgStreamA
 //   V   down: residual of level l restricted to level l+1 (thread per coarse cell, gather over its 2^D children) + Jacobi
 //       from zero; top: a few more sweeps; up: over-corrected prolongation fused with the post-smoothing sweep
 //   2b  z = z0 + e0[cell(row)] ; r.z  -> barrier
+constexpr int kRowTiles = 4; // 32-row tiles whose loads a warp keeps in flight together in the row passes
+
 template<bool FIRST>
 __device__ __forceinline__ double pcg_rows_a(const CgStreamArgs& a, const MgArgs& m, const uint64_t rb, const uint64_t re, const double alpha, double2* __restrict__ zt)
 {
@@ -844,50 +848,78 @@ __device__ __forceinline__ double pcg_rows_a(const CgStreamArgs& a, const MgArgs
 	const double* __restrict__ dinv_c = m.lv[0].dinv;
 	double* __restrict__ rc = m.lv[0].r;
 	double* __restrict__ ec = m.lv[0].e0;
-	double local = 0.0, carry = 0.0;
+	double local = 0.0, carry = 0.0, carry_dc = 0.0;
 	uint32_t carry_id = kMgNone;
-	for (uint64_t base = rb; base < re; base += 32) // warp-uniform trip count
+	for (uint64_t base = rb; base < re; base += 32ull * kRowTiles) // warp-uniform trip count
 	{
-		const uint64_t i = base + lane;
-		const bool on = i < re;
-		double ri = 0.0;
-		uint32_t id = kMgNone;
-		if (on)
-		{
-			id = __ldg(m.crow + i);
-			if (FIRST) ri = __ldcg(m.r + i);
-			else
-			{
-				const double pi = __ldcg(&zt[i].y), api = __ldcg(a.ap + i);
-				a.x[i] = fma(alpha, pi, __ldcg(a.x + i));
-				ri = fma(-alpha, api, __ldcg(m.r + i));
-				m.r[i] = ri;
-			}
-			zt[i].x = ri * __ldg(m.dinv0 + i);
-			local = fma(ri, ri, local);
-		}
-		// inclusive sums of r inside every run of equal cell ids (ids never decrease along the rows)
-		double v = ri;
+		// all loads of the batch first: the pass is bound by L2 latency, not by arithmetic
+		double rv[kRowTiles], pv[kRowTiles], av[kRowTiles], xv[kRowTiles], dv[kRowTiles], dc[kRowTiles];
+		uint32_t id[kRowTiles];
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
+		for (int q = 0; q < kRowTiles; q++)
 		{
-			const double vu = __shfl_up_sync(0xffffffffu, v, o);
-			const uint32_t iu = __shfl_up_sync(0xffffffffu, id, o);
-			if (lane >= static_cast<unsigned>(o) && iu == id) v += vu;
+			const uint64_t i = base + 32ull * q + lane;
+			const bool on = i < re;
+			id[q] = on ? __ldg(m.crow + i) : kMgNone;
+			dv[q] = on ? __ldg(m.dinv0 + i) : 0.0;
+			rv[q] = on ? __ldcg(m.r + i) : 0.0;
+			if (!FIRST)
+			{
+				pv[q] = on ? __ldcg(&zt[i].y) : 0.0; av[q] = on ? __ldcg(a.ap + i) : 0.0; xv[q] = on ? __ldcg(a.x + i) : 0.0;
+			}
 		}
-		if (carry_id != kMgNone)
+		// damped inverse diagonal of the row's cell (a broadcast load for the lanes of one cell): fetched here, not where a
+		// cell's sum is finished, so that the sums below never wait on memory
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++) dc[q] = (id[q] != kMgNone) ? __ldg(dinv_c + id[q]) : 0.0;
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++)
 		{
-			if (id == carry_id) v += carry;                                  // the cell continues from the previous tile
-			else if (lane == 0) { rc[carry_id] = carry; ec[carry_id] = __ldg(dinv_c + carry_id) * carry; } // it ended exactly there
+			const uint64_t i = base + 32ull * q + lane;
+			if (i < re)
+			{
+				if (!FIRST)
+				{
+					a.x[i] = fma(alpha, pv[q], xv[q]);
+					rv[q] = fma(-alpha, av[q], rv[q]);
+					m.r[i] = rv[q];
+				}
+				zt[i].x = rv[q] * dv[q];
+				local = fma(rv[q], rv[q], local);
+			}
 		}
-		const uint32_t idn = __shfl_down_sync(0xffffffffu, id, 1);
-		const bool tail = on && ((lane == 31) ? (i + 1 == re) : (idn != id));
-		if (tail) { rc[id] = v; ec[id] = __ldg(dinv_c + id) * v; }
-		const double v31 = __shfl_sync(0xffffffffu, v, 31);
-		const uint32_t id31 = __shfl_sync(0xffffffffu, id, 31);
-		const int open31 = __shfl_sync(0xffffffffu, (on && !tail) ? 1 : 0, 31);
-		carry = v31;
-		carry_id = open31 ? id31 : kMgNone;
+		// per-cell sums of r: inclusive sums inside every run of equal cell ids (rows of one cell are contiguous), tile by tile,
+		// a cell that crosses a tile boundary carried in (carry, carry_id)
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++)
+		{
+			const uint64_t t0 = base + 32ull * q;
+			if (t0 >= re) break; // warp-uniform
+			const uint64_t i = t0 + lane;
+			const bool on = i < re;
+			double v = rv[q];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const double vu = __shfl_up_sync(0xffffffffu, v, o);
+				const uint32_t iu = __shfl_up_sync(0xffffffffu, id[q], o);
+				if (lane >= static_cast<unsigned>(o) && iu == id[q]) v += vu;
+			}
+			if (carry_id != kMgNone)
+			{
+				if (id[q] == carry_id) v += carry;                               // the cell continues from the previous tile
+				else if (lane == 0) { rc[carry_id] = carry; ec[carry_id] = carry_dc * carry; } // it ended exactly there
+			}
+			const uint32_t idn = __shfl_down_sync(0xffffffffu, id[q], 1);
+			const bool tail = on && ((lane == 31) ? (i + 1 == re) : (idn != id[q]));
+			if (tail) { rc[id[q]] = v; ec[id[q]] = dc[q] * v; }
+			const double v31 = __shfl_sync(0xffffffffu, v, 31);
+			const uint32_t id31 = __shfl_sync(0xffffffffu, id[q], 31);
+			const int open31 = __shfl_sync(0xffffffffu, (on && !tail) ? 1 : 0, 31);
+			carry_dc = __shfl_sync(0xffffffffu, dc[q], 31);
+			carry = v31;
+			carry_id = open31 ? id31 : kMgNone;
+		}
 	}
 	return local;
 }
@@ -896,100 +928,184 @@ __device__ __forceinline__ double pcg_rows_b(const MgArgs& m, const uint64_t rb,
 {
 	const unsigned lane = threadIdx.x & 31;
 	double local = 0.0;
-	for (uint64_t i = rb + lane; i < re; i += 32)
+	for (uint64_t base = rb; base < re; base += 32ull * kRowTiles)
 	{
-		const double z = __ldcg(&zt[i].x) + __ldcg(ef + __ldg(m.crow + i));
-		zt[i].x = z;
-		local = fma(__ldcg(m.r + i), z, local);
+		double zv[kRowTiles], rv[kRowTiles], ev[kRowTiles];
+		uint32_t id[kRowTiles];
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++)
+		{
+			const uint64_t i = base + 32ull * q + lane;
+			const bool on = i < re;
+			id[q] = on ? __ldg(m.crow + i) : kMgNone;
+			zv[q] = on ? __ldcg(&zt[i].x) : 0.0;
+			rv[q] = on ? __ldcg(m.r + i) : 0.0;
+		}
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++) ev[q] = (id[q] != kMgNone) ? __ldcg(ef + id[q]) : 0.0;
+#pragma unroll
+		for (int q = 0; q < kRowTiles; q++)
+		{
+			const uint64_t i = base + 32ull * q + lane;
+			if (i < re)
+			{
+				const double z = zv[q] + ev[q];
+				zt[i].x = z;
+				local = fma(rv[q], z, local);
+			}
+		}
 	}
 	return local;
 }
 
-// One V(1,1) cycle on the cell hierarchy; on entry lv[0].r and lv[0].e0 = dinv r are complete and visible (the r.r barrier),
-// on return (after a grid barrier) the result is in the returned buffer of level 0.  K = 3^D, CH = 2^D.
-__device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const int L, const int K, const int CH,
-	unsigned long long& bar_target, const unsigned nblocks)
+// sum_s S[s] * e[nbr[s]] over the 3^D stencil of one cell, loads issued nine at a time
+template<int K>
+__device__ __forceinline__ double stencil_dot(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const double* __restrict__ e)
 {
+	double acc = 0.0;
+#pragma unroll
+	for (int g = 0; g < K; g += 9)
+	{
+		uint32_t j[9]; double sc[9], v[9];
+#pragma unroll
+		for (int u = 0; u < 9; u++) { j[u] = __ldg(nb + g + u); sc[u] = __ldg(sv + g + u); }
+#pragma unroll
+		for (int u = 0; u < 9; u++) v[u] = (j[u] != kMgNone) ? __ldcg(e + j[u]) : 0.0;
+#pragma unroll
+		for (int u = 0; u < 9; u++) acc = fma(sc[u], v[u], acc);
+	}
+	return acc;
+}
+// the same with the over-corrected prolongation formed on the fly: e[j] + gamma * ehi[parent[j]]
+template<int K>
+__device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const double* __restrict__ e,
+	const double* __restrict__ ehi, const uint32_t* __restrict__ parent, const double gamma)
+{
+	double acc = 0.0;
+#pragma unroll
+	for (int g = 0; g < K; g += 9)
+	{
+		uint32_t j[9], pj[9]; double sc[9], v[9], vh[9];
+#pragma unroll
+		for (int u = 0; u < 9; u++) { j[u] = __ldg(nb + g + u); sc[u] = __ldg(sv + g + u); }
+#pragma unroll
+		for (int u = 0; u < 9; u++) { const bool ok = j[u] != kMgNone; v[u] = ok ? __ldcg(e + j[u]) : 0.0; pj[u] = ok ? __ldg(parent + j[u]) : kMgNone; }
+#pragma unroll
+		for (int u = 0; u < 9; u++) vh[u] = (pj[u] != kMgNone) ? __ldcg(ehi + pj[u]) : 0.0;
+#pragma unroll
+		for (int u = 0; u < 9; u++) acc = fma(sc[u], fma(gamma, vh[u], v[u]), acc);
+	}
+	return acc;
+}
+
+constexpr uint32_t kMgSmallCells = 256;  // levels with at most this many cells are run by CTA 0 alone between block barriers
+
+// One V(1,1) cycle on the cell hierarchy; on entry lv[0].r and lv[0].e0 = dinv r are complete and visible (the r.r barrier),
+// on return (after a grid barrier) the result is in the returned buffer of level 0.
+// Levels [0, Ls) are "wide": every thread of the grid takes cells, one grid barrier per level and direction.  Levels [Ls, L) are
+// small (a few hundred cells): there a grid barrier (~1.5 us + the L2 latency of the stage behind it) would cost far more than the
+// work, so CTA 0 runs them alone between block barriers while the other CTAs wait at the grid barrier that hands the result back.
+template<int D>
+__device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const int L, const int Ls,
+	unsigned long long& bar_target, const unsigned nblocks, unsigned long long* vprof)
+{
+	constexpr int K = (D == 3) ? 27 : 9, CH = 1 << D;
+	const bool cta0 = blockIdx.x == 0;
+	long long tp = vprof ? clock64() : 0;
+	auto lap = [&](const int slot) { if (vprof) { const long long t = clock64(); vprof[slot] += static_cast<unsigned long long>(t - tp); tp = t; } };
 	const uint64_t gt = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, gs = static_cast<uint64_t>(nblocks) * blockDim.x;
 	const double gamma = m.gamma;
 	// ---- down: r_{l+1} = R (r_l - A_l e_l), e_{l+1} = dinv r_{l+1} ----
 	for (int l = 0; l + 1 < L; l++)
 	{
-		const MgLevelPtrs& lo = m.lv[l];
-		const MgLevelPtrs& hi = m.lv[l + 1];
-		const uint64_t nhi = *hi.count;
-		for (uint64_t C = gt; C < nhi; C += gs)
+		const bool wide = (l + 1 < Ls);
+		if (wide || cta0)
 		{
-			double sum = 0.0;
-			for (int q = 0; q < CH; q++)
+			const MgLevelPtrs& lo = m.lv[l];
+			const MgLevelPtrs& hi = m.lv[l + 1];
+			const uint64_t nhi = *hi.count;
+			// CH lanes per coarse cell, one child each (the children's stencil products are independent chains of L2 round trips:
+			// side by side instead of one after the other), summed over the lanes in a fixed order
+			const uint64_t first = (wide ? gt : threadIdx.x) / CH, step = (wide ? gs : blockDim.x) / CH; // gs, blockDim.x are multiples of 32
+			const unsigned q = threadIdx.x % CH;
+			for (uint64_t C0 = 0; C0 < nhi; C0 += step) // warp-uniform trip count
 			{
-				const uint32_t c = __ldg(hi.child + C * CH + q);
-				if (c == kMgNone) continue;
-				double res = __ldcg(lo.r + c);
-				const uint32_t* __restrict__ nb = lo.nbr + static_cast<uint64_t>(c) * K;
-				const double* __restrict__ sv = lo.S + static_cast<uint64_t>(c) * K;
-				for (int s = 0; s < K; s++)
+				const uint64_t C = C0 + first;
+				const bool on = C < nhi;
+				const uint32_t ch = on ? __ldg(hi.child + C * CH + q) : kMgNone;
+				double res = 0.0;
+				if (ch != kMgNone)
 				{
-					const uint32_t j = __ldg(nb + s);
-					if (j != kMgNone) res = fma(-__ldg(sv + s), __ldcg(lo.e0 + j), res);
+					const uint64_t c = ch;
+					res = __ldcg(lo.r + c) - stencil_dot<K>(lo.nbr + c * K, lo.S + c * K, lo.e0);
 				}
-				sum += res;
+#pragma unroll
+				for (int o = 1; o < CH; o <<= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+				if (on && q == 0)
+				{
+					hi.r[C] = res;
+					hi.e0[C] = __ldg(hi.dinv + C) * res;
+				}
 			}
-			hi.r[C] = sum;
-			hi.e0[C] = __ldg(hi.dinv + C) * sum;
 		}
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		else if (cta0) __syncthreads();
+		lap(l);
 	}
 	// ---- top level: more damped-Jacobi sweeps, ping-pong ----
 	const MgLevelPtrs& top = m.lv[L - 1];
-	const uint64_t ntop = *top.count;
 	int cur = 0;
-	for (int t = 0; t < m.top_sweeps; t++)
 	{
-		const double* __restrict__ src = cur ? top.e1 : top.e0;
-		double* __restrict__ dst = cur ? top.e0 : top.e1;
-		for (uint64_t c = gt; c < ntop; c += gs)
+		const bool wide = (L - 1 < Ls);
+		const uint64_t ntop = *top.count;
+		for (int t = 0; t < m.top_sweeps; t++)
 		{
-			double acc = __ldcg(top.r + c);
-			for (int s = 0; s < K; s++)
+			if (wide || cta0)
 			{
-				const uint32_t j = __ldg(top.nbr + c * K + s);
-				if (j != kMgNone) acc = fma(-__ldg(top.S + c * K + s), __ldcg(src + j), acc);
+				const double* __restrict__ src = cur ? top.e1 : top.e0;
+				double* __restrict__ dst = cur ? top.e0 : top.e1;
+				for (uint64_t c = wide ? gt : threadIdx.x; c < ntop; c += wide ? gs : blockDim.x)
+				{
+					const double acc = __ldcg(top.r + c) - stencil_dot<K>(top.nbr + c * K, top.S + c * K, src);
+					dst[c] = fma(__ldg(top.dinv + c), acc, __ldcg(src + c));
+				}
 			}
-			dst[c] = fma(__ldg(top.dinv + c), acc, __ldcg(src + c));
+			if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+			else if (cta0) __syncthreads();
+			cur ^= 1;
 		}
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-		cur ^= 1;
+		lap(16);
 	}
 	const double* ehi = cur ? top.e1 : top.e0;
 	// ---- up: e_l <- e_l + gamma P e_{l+1}, then one Jacobi sweep; the prolongated neighbours are formed on the fly ----
+	bool handed = (L - 1 < Ls); // no small level: nothing to hand back
 	for (int l = L - 2; l >= 0; l--)
 	{
-		const MgLevelPtrs& lv = m.lv[l];
-		const uint64_t nl = *lv.count;
-		for (uint64_t c = gt; c < nl; c += gs)
+		const bool wide = (l < Ls);
+		if (wide && !handed) { grid_barrier(&a.sc->grid_barrier, bar_target, nblocks); handed = true; lap(17); } // CTA 0's small levels -> everybody
+		if (wide || cta0)
 		{
-			double acc = __ldcg(lv.r + c);
-			for (int s = 0; s < K; s++)
+			const MgLevelPtrs& lv = m.lv[l];
+			const uint64_t nl = *lv.count;
+			for (uint64_t c = wide ? gt : threadIdx.x; c < nl; c += wide ? gs : blockDim.x)
 			{
-				const uint32_t j = __ldg(lv.nbr + c * K + s);
-				if (j != kMgNone)
-				{
-					const double ej = fma(gamma, __ldcg(ehi + __ldg(lv.parent + j)), __ldcg(lv.e0 + j));
-					acc = fma(-__ldg(lv.S + c * K + s), ej, acc);
-				}
+				const double acc = __ldcg(lv.r + c) - stencil_dot_prolong<K>(lv.nbr + c * K, lv.S + c * K, lv.e0, ehi, lv.parent, gamma);
+				const double ecur = fma(gamma, __ldcg(ehi + __ldg(lv.parent + c)), __ldcg(lv.e0 + c));
+				lv.e1[c] = fma(__ldg(lv.dinv + c), acc, ecur);
 			}
-			const double ec = fma(gamma, __ldcg(ehi + __ldg(lv.parent + c)), __ldcg(lv.e0 + c));
-			lv.e1[c] = fma(__ldg(lv.dinv + c), acc, ec);
 		}
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-		ehi = lv.e1;
+		if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		else if (cta0) __syncthreads();
+		ehi = m.lv[l].e1;
+		lap(20 + l);
 	}
+	if (!handed) { grid_barrier(&a.sc->grid_barrier, bar_target, nblocks); lap(17); }
 	return ehi;
 }
 
-template<int LPR>
-__global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m, int K, int CH)
+// 2-D runs 8 consumer warps + the producer (cg_configure caps it there): the smaller bound leaves the row passes their registers
+template<int LPR, int D>
+__global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	if (*reinterpret_cast<volatile int*>(&a.sc->error) != 0) return; // see k_cg_stream
@@ -1009,10 +1125,14 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStream
 	const bool prof_on = (a.prof != nullptr) && (threadIdx.x == 0);
 	const bool meas_on = (a.cta_meas != nullptr) && (threadIdx.x == 0);
 	unsigned long long spmv_cycles = 0;
+	// per-stage cycle counters of the preconditioner as CTA 0 sees them (behind the per-CTA counters; mps_get_cg_profile_stages)
+	unsigned long long* vprof = (prof_on && blockIdx.x == 0) ? a.prof + static_cast<size_t>(nblocks) * 8 : nullptr;
 
 	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA)
 	int L = 1;
 	while (L < m.levels && *m.lv[L - 1].count > m.top_cells) L++;
+	int Ls = 0; // first level small enough for CTA 0 alone
+	while (Ls < L && *m.lv[Ls].count > kMgSmallCells) Ls++;
 	// this warp's rows in phase 2: a cell-aligned range, the level-0 cells split evenly over all warps of the grid
 	uint64_t rb, re;
 	{
@@ -1037,7 +1157,7 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStream
 		// z0 = M^-1 r0
 		pcg_rows_a<true>(a, m, rb, re, 0.0, zprev);
 		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-		const double* ef = mg_vcycle(a, m, L, K, CH, bar_target, nblocks);
+		const double* ef = mg_vcycle<D>(a, m, L, Ls, bar_target, nblocks, vprof);
 		local = pcg_rows_b(m, rb, re, ef, zprev);
 		rz = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
 	}
@@ -1053,8 +1173,11 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStream
 		const double alpha = rz / pAp;
 
 		// ---- phase 2a: x, r, r.r, Jacobi part of z, level-0 residual ----
+		const long long u0 = vprof ? clock64() : 0;
 		local = pcg_rows_a<false>(a, m, rb, re, alpha, zcur);
+		const long long u1 = vprof ? clock64() : 0;
 		const double rr_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		if (vprof) { const long long u2 = clock64(); vprof[40] += static_cast<unsigned long long>(u1 - u0); vprof[42] += static_cast<unsigned long long>(u2 - u1); vprof[43] += static_cast<unsigned long long>(u0 - t1); }
 		iter++;
 		rr = rr_new;
 		converged = (rr_new < tol);            // Computer.hpp:1407-1408
@@ -1062,10 +1185,12 @@ __global__ void __launch_bounds__(kMaxStreamWarps * 32, 1) k_pcg_stream(CgStream
 
 		// ---- coarse part of z and r.z ----
 		const long long t2 = prof_on ? clock64() : 0;
-		const double* ef = mg_vcycle(a, m, L, K, CH, bar_target, nblocks);
+		const double* ef = mg_vcycle<D>(a, m, L, Ls, bar_target, nblocks, vprof);
 		const long long t3 = prof_on ? clock64() : 0;
 		local = pcg_rows_b(m, rb, re, ef, zcur);
+		const long long u3 = vprof ? clock64() : 0;
 		const double rz_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		if (vprof) { vprof[41] += static_cast<unsigned long long>(u3 - t3); vprof[44] += static_cast<unsigned long long>(clock64() - u3); }
 		if (prof_on)
 		{
 			const long long t4 = clock64();
@@ -1281,6 +1406,7 @@ cudaError_t launch_stream(mps_solver* s)
 		if (e != cudaSuccess) return e;
 		L.a.prof = c.prof.p;
 		c.prof_blocks = L.grid;
+		c.prof_stages = false;
 	}
 	if (c.adaptive)
 	{
@@ -1301,7 +1427,7 @@ cudaError_t launch_stream(mps_solver* s)
 }
 
 // the preconditioned solve (one GPU): same launch geometry as k_cg_stream + the level tables of mps_mg.cu
-template<int LPR>
+template<int LPR, int D>
 cudaError_t launch_pcg(mps_solver* s)
 {
 	CgBuffers& c = s->cg;
@@ -1320,23 +1446,23 @@ cudaError_t launch_pcg(mps_solver* s)
 		q.count = b.rank.p + b.dense; q.S = b.S.p; q.nbr = b.nbr.p; q.dinv = b.dinv.p; q.child = b.child.p; q.parent = b.parent.p;
 		q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p;
 	}
-	int K = (s->env.dim == 3) ? 27 : 9, CH = 1 << s->env.dim;
-	e = cudaFuncSetAttribute(k_pcg_stream<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	e = cudaFuncSetAttribute(k_pcg_stream<LPR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_stream<LPR>, L.threads, L.smem_bytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_stream<LPR, D>, L.threads, L.smem_bytes);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
 	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
 	if (e != cudaSuccess) return e;
 	if (s->cg_profile)
 	{
-		e = c.prof.ensure(8ull * L.grid, s->stream);
+		e = c.prof.ensure(8ull * L.grid + kProfStages, s->stream);
 		if (e != cudaSuccess) return e;
-		e = cudaMemsetAsync(c.prof.p, 0, 8ull * L.grid * sizeof(unsigned long long), s->stream);
+		e = cudaMemsetAsync(c.prof.p, 0, (8ull * L.grid + kProfStages) * sizeof(unsigned long long), s->stream);
 		if (e != cudaSuccess) return e;
 		L.a.prof = c.prof.p;
 		c.prof_blocks = L.grid;
+		c.prof_stages = true;
 	}
 	if (c.adaptive)
 	{
@@ -1344,9 +1470,9 @@ cudaError_t launch_pcg(mps_solver* s)
 		if (e != cudaSuccess) return e;
 		L.a.cta_meas = c.cta_meas.p;
 	}
-	void* params[] = { &L.a, &m, &K, &CH };
+	void* params[] = { &L.a, &m };
 	s->stats.kernel_launches += 1;
-	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_stream<LPR>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_stream<LPR, D>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
 	if (e != cudaSuccess) return e;
 	if (c.adaptive)
 	{
@@ -1356,16 +1482,18 @@ cudaError_t launch_pcg(mps_solver* s)
 	return cudaGetLastError();
 }
 
-cudaError_t launch_pcg_lpr(mps_solver* s)
+template<int D>
+cudaError_t launch_pcg_dim(mps_solver* s)
 {
 	switch (s->cg.lanes_per_row)
 	{
-	case 1: return launch_pcg<1>(s);
-	case 2: return launch_pcg<2>(s);
-	case 4: return launch_pcg<4>(s);
-	default: return launch_pcg<8>(s);
+	case 1: return launch_pcg<1, D>(s);
+	case 2: return launch_pcg<2, D>(s);
+	case 4: return launch_pcg<4, D>(s);
+	default: return launch_pcg<8, D>(s);
 	}
 }
+cudaError_t launch_pcg_lpr(mps_solver* s) { return s->env.dim == 3 ? launch_pcg_dim<3>(s) : launch_pcg_dim<2>(s); }
 
 template<bool MG>
 cudaError_t launch_stream_lpr(mps_solver* s)
@@ -1492,6 +1620,7 @@ cudaError_t cg_configure(mps_solver* s)
 	warps = warps / static_cast<int>(kGroups) * static_cast<int>(kGroups);
 	if (warps < static_cast<int>(kGroups)) warps = kGroups;
 	if (warps > kMaxStreamWarps - 1) warps = kMaxStreamWarps - 1;
+	if (D == 2 && warps > kStreamWarps2d - 1) warps = kStreamWarps2d - 1;
 	c.consumer_warps = warps;
 	c.lanes_per_row = (D == 3) ? 4 : 1;
 	if (const char* v = std::getenv("MPS_CG_LPR")) { const int w = std::atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) c.lanes_per_row = w; }

@@ -83,6 +83,7 @@ struct CgBuffers
 	CgStepScalars* h_step = nullptr; // ... and their pinned host mirror (convergence test)
 	DevBuf<unsigned long long> prof; // per-CTA cycle counters of the last streaming solve (mps_get_cg_profile)
 	unsigned prof_blocks = 0;
+	bool prof_stages = false;        // prof holds 64 per-stage counters of the preconditioned solve behind the per-CTA ones
 };
 
 // multigrid preconditioner of the PPE solve: per-level device buffers (mps_mg.cu)

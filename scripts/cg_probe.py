@@ -27,6 +27,11 @@ if it:
         m["iteration_cycles_total"] / it))
     print("preconditioner: levels %d, cells %d, matrix sweeps %d" % (st["mg_levels"], st["mg_cells"], st["matrix_sweeps"]))
 
+stg = gpu.cg_profile_stages().astype(float)
+if it and stg.sum() > 0:
+    us = stg / it / 1.965e3   # cycles per iteration -> microseconds at 1965 MHz
+    print("CTA 0, us per iteration: down " + " ".join(f"{v:.1f}" for v in us[0:st["mg_levels"] - 1]) + f" | top {us[16]:.1f} | hand-back wait {us[17]:.1f} | up "
+          + " ".join(f"{v:.1f}" for v in us[20:20 + st["mg_levels"] - 1]) + f" | rows 2a {us[40]:.1f} 2b {us[41]:.1f} | reductions pAp {us[43]:.1f} rr {us[42]:.1f} rz {us[44]:.1f}")
 raw = gpu.cg_profile_raw().astype(float)
 if len(raw) and it:
     import numpy as np

@@ -345,6 +345,7 @@ __device__ __forceinline__ double all_sum(const CgStreamArgs& a, double local, d
 	}
 	const PeerLink& pl = a.peer;
 	seq++;
+	bar_target += nblocks - 1; // every thread keeps the same count: plain grid barriers on the same counter may follow (k_pcg_stream)
 	const unsigned long long want = pl.tag | seq;
 	const unsigned slot = static_cast<unsigned>(seq & 3ull);
 	PeerMail* bc = pl.mail[pl.rank] + 4 * kMaxPeerRanks + slot; // the total, published by CTA 0 to the other CTAs of this grid
@@ -369,7 +370,6 @@ __device__ __forceinline__ double all_sum(const CgStreamArgs& a, double local, d
 		else
 		{
 			// CTA 0: wait for the other CTAs of this grid, add the partials in a fixed order, exchange the sum with the other ranks
-			bar_target += nblocks - 1;
 			if (lane == 0)
 			{
 				part[0] = local;
@@ -958,9 +958,29 @@ __device__ __forceinline__ double pcg_rows_b(const MgArgs& m, const uint64_t rb,
 	return local;
 }
 
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
+{
+	double v;
+	asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+	return v;
+}
+// One level vector as a rank sees it.  One GPU / replicated level: the whole vector is local.  Distributed level: cells [lo, hi)
+// are this rank's (local, L2); a stencil or a prolongation may also touch the first cells behind either end, which belong to the
+// adjacent rank and are read straight from its arena over NVLink (strong system-scope loads: never from a stale local cache line).
+template<bool HALO>
+struct LevelView
+{
+	const double* loc; const double* left; const double* right;
+	uint32_t lo, hi;
+	__device__ __forceinline__ double ld(const uint32_t j) const
+	{
+		if (!HALO || (j >= lo && j < hi)) return __ldcg(loc + j);
+		return ld_relaxed_sys_f64(((j < lo) ? left : right) + j);
+	}
+};
 // sum_s S[s] * e[nbr[s]] over the 3^D stencil of one cell, loads issued nine at a time
-template<int K>
-__device__ __forceinline__ double stencil_dot(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const double* __restrict__ e)
+template<int K, bool HALO>
+__device__ __forceinline__ double stencil_dot(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const LevelView<HALO>& e)
 {
 	double acc = 0.0;
 #pragma unroll
@@ -970,16 +990,16 @@ __device__ __forceinline__ double stencil_dot(const uint32_t* __restrict__ nb, c
 #pragma unroll
 		for (int u = 0; u < 9; u++) { j[u] = __ldg(nb + g + u); sc[u] = __ldg(sv + g + u); }
 #pragma unroll
-		for (int u = 0; u < 9; u++) v[u] = (j[u] != kMgNone) ? __ldcg(e + j[u]) : 0.0;
+		for (int u = 0; u < 9; u++) v[u] = (j[u] != kMgNone) ? e.ld(j[u]) : 0.0;
 #pragma unroll
 		for (int u = 0; u < 9; u++) acc = fma(sc[u], v[u], acc);
 	}
 	return acc;
 }
 // the same with the over-corrected prolongation formed on the fly: e[j] + gamma * ehi[parent[j]]
-template<int K>
-__device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const double* __restrict__ e,
-	const double* __restrict__ ehi, const uint32_t* __restrict__ parent, const double gamma)
+template<int K, bool HALO, bool HALO_HI>
+__device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict__ nb, const double* __restrict__ sv, const LevelView<HALO>& e,
+	const LevelView<HALO_HI>& ehi, const uint32_t* __restrict__ parent, const double gamma)
 {
 	double acc = 0.0;
 #pragma unroll
@@ -989,9 +1009,9 @@ __device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict
 #pragma unroll
 		for (int u = 0; u < 9; u++) { j[u] = __ldg(nb + g + u); sc[u] = __ldg(sv + g + u); }
 #pragma unroll
-		for (int u = 0; u < 9; u++) { const bool ok = j[u] != kMgNone; v[u] = ok ? __ldcg(e + j[u]) : 0.0; pj[u] = ok ? __ldg(parent + j[u]) : kMgNone; }
+		for (int u = 0; u < 9; u++) { const bool ok = j[u] != kMgNone; v[u] = ok ? e.ld(j[u]) : 0.0; pj[u] = ok ? __ldg(parent + j[u]) : kMgNone; }
 #pragma unroll
-		for (int u = 0; u < 9; u++) vh[u] = (pj[u] != kMgNone) ? __ldcg(ehi + pj[u]) : 0.0;
+		for (int u = 0; u < 9; u++) vh[u] = (pj[u] != kMgNone) ? ehi.ld(pj[u]) : 0.0;
 #pragma unroll
 		for (int u = 0; u < 9; u++) acc = fma(sc[u], fma(gamma, vh[u], v[u]), acc);
 	}
@@ -1000,14 +1020,51 @@ __device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict
 
 constexpr uint32_t kMgSmallCells = 256;  // levels with at most this many cells are run by CTA 0 alone between block barriers
 
+// several ranks: which compact cells of level l lie left of cell column `col` (slab boundaries are multiples of 2^l columns for
+// every level this is asked for, MgDist)
+__device__ __forceinline__ uint32_t level_cell_begin(const MgLevelPtrs& lv, const int l, const uint32_t col)
+{
+	uint64_t idx = static_cast<uint64_t>(col >> l) * lv.colstride;
+	if (idx > lv.dense) idx = lv.dense;
+	return static_cast<uint32_t>(__ldg(lv.ranktab + idx));
+}
+
+// what the V-cycle needs to know about the other ranks (all in registers / shared memory of the CTA)
+struct DistCtx
+{
+	int k;                                 // first replicated level
+	uint32_t lo[kMgMaxDistLevels + 1];     // this rank's cells of levels 0 .. k
+	uint32_t hi[kMgMaxDistLevels + 1];
+	const uint32_t* gather;                // [nranks + 1] (shared memory) cell ranges of every rank at level k
+};
+
+template<bool MG>
+__device__ __forceinline__ LevelView<MG> level_view(const MgArgs& m, const DistCtx& dc, const int l, const int which /* 1: e0, 2: e1 */, const double* loc)
+{
+	LevelView<MG> v;
+	v.loc = loc; v.left = nullptr; v.right = nullptr; v.lo = 0; v.hi = 0xffffffffu;
+	if (MG && l < dc.k)
+	{
+		const uint64_t off = (which == 1) ? m.lv[l].off_e0 : m.lv[l].off_e1;
+		const MgDist& d = m.dist;
+		v.lo = dc.lo[l]; v.hi = dc.hi[l];
+		v.left = (d.rank > 0) ? d.peer_vec[d.rank - 1] + off : loc;
+		v.right = (d.rank + 1 < d.nranks) ? d.peer_vec[d.rank + 1] + off : loc;
+	}
+	return v;
+}
+
 // One V(1,1) cycle on the cell hierarchy; on entry lv[0].r and lv[0].e0 = dinv r are complete and visible (the r.r barrier),
 // on return (after a grid barrier) the result is in the returned buffer of level 0.
 // Levels [0, Ls) are "wide": every thread of the grid takes cells, one grid barrier per level and direction.  Levels [Ls, L) are
 // small (a few hundred cells): there a grid barrier (~1.5 us + the L2 latency of the stage behind it) would cost far more than the
 // work, so CTA 0 runs them alone between block barriers while the other CTAs wait at the grid barrier that hands the result back.
-template<int D>
-__device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const int L, const int Ls,
-	unsigned long long& bar_target, const unsigned nblocks, unsigned long long* vprof)
+// Several ranks (MG): levels [0, k) are distributed — own cells only, halo cells of the adjacent ranks read from their arenas,
+// and the barrier behind such a stage is the cross-rank one (all_sum<true> of nothing); level k is gathered from all ranks; the
+// levels above run replicated exactly as on one GPU.  On entry the barrier the caller went through must have been cross-rank.
+template<int D, bool MG>
+__device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const DistCtx& dc, const int L, const int Ls,
+	unsigned long long& bar_target, unsigned long long& seq, unsigned& part_sel, double* red, const unsigned nblocks, unsigned long long* vprof)
 {
 	constexpr int K = (D == 3) ? 27 : 9, CH = 1 << D;
 	const bool cta0 = blockIdx.x == 0;
@@ -1015,29 +1072,56 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 	auto lap = [&](const int slot) { if (vprof) { const long long t = clock64(); vprof[slot] += static_cast<unsigned long long>(t - tp); tp = t; } };
 	const uint64_t gt = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, gs = static_cast<uint64_t>(nblocks) * blockDim.x;
 	const double gamma = m.gamma;
+	auto gbar = [&]() { grid_barrier(&a.sc->grid_barrier, bar_target, nblocks); };
+	auto pbar = [&]() { double* q = a.partials + (part_sel & 1u) * nblocks; part_sel++; all_sum<true>(a, 0.0, q, red, bar_target, seq, nblocks); };
+	// level k of every rank -> here (r and e0: what the replicated part starts from)
+	auto gather_level = [&](const int k)
+	{
+		const MgDist& d = m.dist;
+		const MgLevelPtrs& lv = m.lv[k];
+		for (int r = 0; r < d.nranks; r++)
+		{
+			if (r == d.rank) continue;
+			const double* __restrict__ pr = d.peer_vec[r] + lv.off_r;
+			const double* __restrict__ pe = d.peer_vec[r] + lv.off_e0;
+			const uint64_t b = dc.gather[r], e = dc.gather[r + 1];
+			for (uint64_t c = b + gt; c < e; c += 4 * gs)
+			{
+				double vr[4], ve[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) { const uint64_t j = c + u * gs; vr[u] = (j < e) ? ld_relaxed_sys_f64(pr + j) : 0.0; ve[u] = (j < e) ? ld_relaxed_sys_f64(pe + j) : 0.0; }
+#pragma unroll
+				for (int u = 0; u < 4; u++) { const uint64_t j = c + u * gs; if (j < e) { lv.r[j] = vr[u]; lv.e0[j] = ve[u]; } }
+			}
+		}
+		gbar();
+	};
+	if (MG && dc.k == 0) { gather_level(0); lap(18); }
 	// ---- down: r_{l+1} = R (r_l - A_l e_l), e_{l+1} = dinv r_{l+1} ----
 	for (int l = 0; l + 1 < L; l++)
 	{
 		const bool wide = (l + 1 < Ls);
+		const bool owned = MG && (l + 1 <= dc.k); // the result level is distributed or about to be gathered: own cells only
 		if (wide || cta0)
 		{
 			const MgLevelPtrs& lo = m.lv[l];
 			const MgLevelPtrs& hi = m.lv[l + 1];
-			const uint64_t nhi = *hi.count;
+			const uint64_t c_b = owned ? dc.lo[l + 1] : 0, c_e = owned ? dc.hi[l + 1] : *hi.count;
+			const LevelView<MG> ev = level_view<MG>(m, dc, l, 1, lo.e0);
 			// CH lanes per coarse cell, one child each (the children's stencil products are independent chains of L2 round trips:
 			// side by side instead of one after the other), summed over the lanes in a fixed order
 			const uint64_t first = (wide ? gt : threadIdx.x) / CH, step = (wide ? gs : blockDim.x) / CH; // gs, blockDim.x are multiples of 32
 			const unsigned q = threadIdx.x % CH;
-			for (uint64_t C0 = 0; C0 < nhi; C0 += step) // warp-uniform trip count
+			for (uint64_t C0 = c_b; C0 < c_e; C0 += step) // warp-uniform trip count
 			{
 				const uint64_t C = C0 + first;
-				const bool on = C < nhi;
+				const bool on = C < c_e;
 				const uint32_t ch = on ? __ldg(hi.child + C * CH + q) : kMgNone;
 				double res = 0.0;
 				if (ch != kMgNone)
 				{
 					const uint64_t c = ch;
-					res = __ldcg(lo.r + c) - stencil_dot<K>(lo.nbr + c * K, lo.S + c * K, lo.e0);
+					res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
 				}
 #pragma unroll
 				for (int o = 1; o < CH; o <<= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
@@ -1048,8 +1132,10 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 				}
 			}
 		}
-		if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		if (owned) pbar();
+		else if (wide) gbar();
 		else if (cta0) __syncthreads();
+		if (MG && l + 1 == dc.k) gather_level(dc.k);
 		lap(l);
 	}
 	// ---- top level: more damped-Jacobi sweeps, ping-pong ----
@@ -1064,13 +1150,14 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 			{
 				const double* __restrict__ src = cur ? top.e1 : top.e0;
 				double* __restrict__ dst = cur ? top.e0 : top.e1;
+				LevelView<false> sv; sv.loc = src;
 				for (uint64_t c = wide ? gt : threadIdx.x; c < ntop; c += wide ? gs : blockDim.x)
 				{
-					const double acc = __ldcg(top.r + c) - stencil_dot<K>(top.nbr + c * K, top.S + c * K, src);
+					const double acc = __ldcg(top.r + c) - stencil_dot<K, false>(top.nbr + c * K, top.S + c * K, sv);
 					dst[c] = fma(__ldg(top.dinv + c), acc, __ldcg(src + c));
 				}
 			}
-			if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+			if (wide) gbar();
 			else if (cta0) __syncthreads();
 			cur ^= 1;
 		}
@@ -1082,34 +1169,39 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 	for (int l = L - 2; l >= 0; l--)
 	{
 		const bool wide = (l < Ls);
-		if (wide && !handed) { grid_barrier(&a.sc->grid_barrier, bar_target, nblocks); handed = true; lap(17); } // CTA 0's small levels -> everybody
+		const bool owned = MG && (l < dc.k);
+		if (wide && !handed) { gbar(); handed = true; lap(17); } // CTA 0's small levels -> everybody
 		if (wide || cta0)
 		{
 			const MgLevelPtrs& lv = m.lv[l];
-			const uint64_t nl = *lv.count;
-			for (uint64_t c = wide ? gt : threadIdx.x; c < nl; c += wide ? gs : blockDim.x)
+			const uint64_t c_b = owned ? dc.lo[l] : 0, c_e = owned ? dc.hi[l] : *lv.count;
+			const LevelView<MG> ev = level_view<MG>(m, dc, l, 1, lv.e0);
+			const LevelView<MG> hv = level_view<MG>(m, dc, l + 1, 2, ehi); // a distributed upper level is never the top: its result is e1
+			for (uint64_t c = c_b + (wide ? gt : threadIdx.x); c < c_e; c += wide ? gs : blockDim.x)
 			{
-				const double acc = __ldcg(lv.r + c) - stencil_dot_prolong<K>(lv.nbr + c * K, lv.S + c * K, lv.e0, ehi, lv.parent, gamma);
-				const double ecur = fma(gamma, __ldcg(ehi + __ldg(lv.parent + c)), __ldcg(lv.e0 + c));
+				const double acc = __ldcg(lv.r + c) - stencil_dot_prolong<K, MG, MG>(lv.nbr + c * K, lv.S + c * K, ev, hv, lv.parent, gamma);
+				const double ecur = fma(gamma, hv.ld(__ldg(lv.parent + c)), __ldcg(lv.e0 + c));
 				lv.e1[c] = fma(__ldg(lv.dinv + c), acc, ecur);
 			}
 		}
-		if (wide) grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		if (owned && l > 0) pbar();      // the level below reads this rank's result as halo
+		else if (wide) gbar();           // (level 0's result is only read by its owner's rows)
 		else if (cta0) __syncthreads();
 		ehi = m.lv[l].e1;
 		lap(20 + l);
 	}
-	if (!handed) { grid_barrier(&a.sc->grid_barrier, bar_target, nblocks); lap(17); }
+	if (!handed) { gbar(); lap(17); }
 	return ehi;
 }
 
 // 2-D runs 8 consumer warps + the producer (cg_configure caps it there): the smaller bound leaves the row passes their registers
-template<int LPR, int D>
+template<int LPR, int D, bool MG>
 __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ uint32_t s_gather[kMaxPeerRanks + 1];
 	if (*reinterpret_cast<volatile int*>(&a.sc->error) != 0) return; // see k_cg_stream
-	const StreamCta cta = stream_setup<true, false>(a, smem_raw);
+	const StreamCta cta = stream_setup<true, MG>(a, smem_raw);
 	const StreamSmem& sm = cta.sm;
 	double* red = cta.red;
 	const uint32_t c0 = cta.c0, c1 = cta.c1, live = cta.live;
@@ -1128,23 +1220,45 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 	// per-stage cycle counters of the preconditioner as CTA 0 sees them (behind the per-CTA counters; mps_get_cg_profile_stages)
 	unsigned long long* vprof = (prof_on && blockIdx.x == 0) ? a.prof + static_cast<size_t>(nblocks) * 8 : nullptr;
 
-	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA)
+	// several ranks: this rank's cells of the distributed levels, every rank's cells of the gathered one
+	DistCtx dc;
+	dc.k = MG ? m.dist.k : 0;
+	dc.gather = s_gather;
+#pragma unroll
+	for (int l = 0; l <= kMgMaxDistLevels; l++) { dc.lo[l] = 0; dc.hi[l] = 0; }
+	if (MG)
+	{
+#pragma unroll
+		for (int l = 0; l <= kMgMaxDistLevels; l++)
+			if (l <= dc.k)
+			{
+				dc.lo[l] = level_cell_begin(m.lv[l], l, m.dist.col_b[m.dist.rank]);
+				dc.hi[l] = level_cell_begin(m.lv[l], l, m.dist.col_b[m.dist.rank + 1]);
+			}
+		if (threadIdx.x <= static_cast<unsigned>(m.dist.nranks)) s_gather[threadIdx.x] = level_cell_begin(m.lv[dc.k], dc.k, m.dist.col_b[threadIdx.x]);
+		__syncthreads();
+	}
+	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA); the gathered
+	// level of a multi-rank run is always one of them
 	int L = 1;
 	while (L < m.levels && *m.lv[L - 1].count > m.top_cells) L++;
+	if (MG && L < dc.k + 1) L = dc.k + 1;
 	int Ls = 0; // first level small enough for CTA 0 alone
 	while (Ls < L && *m.lv[Ls].count > kMgSmallCells) Ls++;
-	// this warp's rows in phase 2: a cell-aligned range, the level-0 cells split evenly over all warps of the grid
+	if (MG && Ls < dc.k + 1) Ls = dc.k + 1; // distributed and gathered levels are always run by the whole grid
+	// this warp's rows in phase 2: a cell-aligned range, this rank's level-0 cells split evenly over all warps of the grid
 	uint64_t rb, re;
 	{
-		const uint64_t cells = *m.lv[0].count;
+		const uint64_t cell_b = MG ? level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank]) : 0;
+		const uint64_t cells = (MG ? level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank + 1]) : *m.lv[0].count) - cell_b;
 		const uint64_t wpb = blockDim.x >> 5, W = static_cast<uint64_t>(nblocks) * wpb, gw = static_cast<uint64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
 		const uint64_t cb = cells / W * gw + cells % W * gw / W, ce = cells / W * (gw + 1) + cells % W * (gw + 1) / W;
-		rb = m.cstart[cb]; re = m.cstart[ce];
+		rb = m.cstart[cell_b + cb]; re = m.cstart[cell_b + ce];
 	}
 
 	// ---- r0 = b - A x ; p_prev = 0 ; rr = r0.r0 (Computer.hpp:1382-1386) ----
-	double local = spmv_phase<LPR, false, false, true>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
-	double rr = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+	double local = spmv_phase<LPR, false, MG, true>(a, sm, c0, c1, live, it, dseq, 0.0, nullptr, a.z0, pol_matrix, pol_vector);
+	double rr = all_sum<MG>(a, local, next_part(), red, bar_target, seq, nblocks);
 	const double rr0 = rr;
 	const double tol = rr * a.eps * a.eps;     // Computer.hpp:1386
 	bool converged = (tol == 0);                // Computer.hpp:1389
@@ -1156,27 +1270,28 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 	{
 		// z0 = M^-1 r0
 		pcg_rows_a<true>(a, m, rb, re, 0.0, zprev);
-		grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
-		const double* ef = mg_vcycle<D>(a, m, L, Ls, bar_target, nblocks, vprof);
+		if (MG) all_sum<true>(a, 0.0, next_part(), red, bar_target, seq, nblocks);
+		else grid_barrier(&a.sc->grid_barrier, bar_target, nblocks);
+		const double* ef = mg_vcycle<D, MG>(a, m, dc, L, Ls, bar_target, seq, part_sel, red, nblocks, vprof);
 		local = pcg_rows_b(m, rb, re, ef, zprev);
-		rz = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		rz = all_sum<MG>(a, local, next_part(), red, bar_target, seq, nblocks);
 	}
 
 	while (iter < n && !converged)
 	{
 		// ---- phase 1: p = z + beta p_prev ; Ap = A p ; p.Ap ----
 		const long long t0 = (prof_on || meas_on) ? clock64() : 0;
-		local = spmv_phase<LPR, true, false>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
+		local = spmv_phase<LPR, true, MG>(a, sm, c0, c1, live, it, dseq, beta, zprev, zcur, pol_matrix, pol_vector);
 		const long long t1 = (prof_on || meas_on) ? clock64() : 0;
 		spmv_cycles += static_cast<unsigned long long>(t1 - t0);
-		const double pAp = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		const double pAp = all_sum<MG>(a, local, next_part(), red, bar_target, seq, nblocks);
 		const double alpha = rz / pAp;
 
 		// ---- phase 2a: x, r, r.r, Jacobi part of z, level-0 residual ----
 		const long long u0 = vprof ? clock64() : 0;
 		local = pcg_rows_a<false>(a, m, rb, re, alpha, zcur);
 		const long long u1 = vprof ? clock64() : 0;
-		const double rr_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		const double rr_new = all_sum<MG>(a, local, next_part(), red, bar_target, seq, nblocks);
 		if (vprof) { const long long u2 = clock64(); vprof[40] += static_cast<unsigned long long>(u1 - u0); vprof[42] += static_cast<unsigned long long>(u2 - u1); vprof[43] += static_cast<unsigned long long>(u0 - t1); }
 		iter++;
 		rr = rr_new;
@@ -1185,11 +1300,11 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 
 		// ---- coarse part of z and r.z ----
 		const long long t2 = prof_on ? clock64() : 0;
-		const double* ef = mg_vcycle<D>(a, m, L, Ls, bar_target, nblocks, vprof);
+		const double* ef = mg_vcycle<D, MG>(a, m, dc, L, Ls, bar_target, seq, part_sel, red, nblocks, vprof);
 		const long long t3 = prof_on ? clock64() : 0;
 		local = pcg_rows_b(m, rb, re, ef, zcur);
 		const long long u3 = vprof ? clock64() : 0;
-		const double rz_new = all_sum<false>(a, local, next_part(), red, bar_target, seq, nblocks);
+		const double rz_new = all_sum<MG>(a, local, next_part(), red, bar_target, seq, nblocks);
 		if (vprof) { vprof[41] += static_cast<unsigned long long>(u3 - t3); vprof[44] += static_cast<unsigned long long>(clock64() - u3); }
 		if (prof_on)
 		{
@@ -1426,8 +1541,9 @@ cudaError_t launch_stream(mps_solver* s)
 	return cudaGetLastError();
 }
 
-// the preconditioned solve (one GPU): same launch geometry as k_cg_stream + the level tables of mps_mg.cu
-template<int LPR, int D>
+// the preconditioned solve: same launch geometry as k_cg_stream + the level tables of mps_mg.cu.  MG (several ranks over peer
+// memory): the level vectors live in the "mg" section of every rank's arena (MgDist, mps_device.cuh)
+template<int LPR, int D, bool MG>
 cudaError_t launch_pcg(mps_solver* s)
 {
 	CgBuffers& c = s->cg;
@@ -1435,21 +1551,40 @@ cudaError_t launch_pcg(mps_solver* s)
 	StreamLaunch L;
 	cudaError_t e = prepare_stream(s, L);
 	if (e != cudaSuccess) return e;
+	if (MG)
+	{
+		e = comm_prepare_link(s);
+		if (e != cudaSuccess) return e;
+		L.a.peer = s->comm.link;
+	}
 	L.a.r = c.r.p;
 	MgArgs m{};
 	m.levels = g.levels; m.top_sweeps = g.top_sweeps; m.top_cells = g.top_cells; m.gamma = g.gamma;
 	m.crow = g.crow.p; m.cstart = g.cstart.p; m.dinv0 = g.dinv0.p; m.r = c.r.p;
+	double* arena_vec = MG ? comm_mg_section(s, s->comm.rank) : nullptr;
+	if (MG && (!arena_vec || !g.in_arena)) return cudaErrorInvalidValue;
 	for (int l = 0; l < g.levels; l++)
 	{
 		MgLevelBufs& b = g.lv[l];
 		MgLevelPtrs& q = m.lv[l];
 		q.count = b.rank.p + b.dense; q.S = b.S.p; q.nbr = b.nbr.p; q.dinv = b.dinv.p; q.child = b.child.p; q.parent = b.parent.p;
-		q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p;
+		q.ranktab = b.rank.p; q.colstride = b.dense / static_cast<uint64_t>(b.dims[0]); q.dense = b.dense;
+		q.off_r = g.vec_off[l][0]; q.off_e0 = g.vec_off[l][1]; q.off_e1 = g.vec_off[l][2];
+		if (MG) { q.r = arena_vec + q.off_r; q.e0 = arena_vec + q.off_e0; q.e1 = arena_vec + q.off_e1; }
+		else { q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p; }
 	}
-	e = cudaFuncSetAttribute(k_pcg_stream<LPR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
+	if (MG)
+	{
+		MgDist& d = m.dist;
+		d.on = 1; d.k = g.k_dist; d.rank = s->comm.rank; d.nranks = s->comm.nranks;
+		if (!s->slabs_set()) return cudaErrorInvalidValue;
+		for (int r = 0; r <= d.nranks; r++) d.col_b[r] = s->col_b[r];
+		for (int r = 0; r < d.nranks; r++) { d.peer_vec[r] = comm_mg_section(s, r); if (!d.peer_vec[r]) return cudaErrorInvalidValue; }
+	}
+	e = cudaFuncSetAttribute(k_pcg_stream<LPR, D, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes));
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_stream<LPR, D>, L.threads, L.smem_bytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_stream<LPR, D, MG>, L.threads, L.smem_bytes);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
 	e = cudaMemsetAsync(&s->d_sc->grid_barrier, 0, sizeof(unsigned long long), s->stream);
@@ -1472,7 +1607,7 @@ cudaError_t launch_pcg(mps_solver* s)
 	}
 	void* params[] = { &L.a, &m };
 	s->stats.kernel_launches += 1;
-	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_stream<LPR, D>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
+	e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_stream<LPR, D, MG>), dim3(L.grid), dim3(L.threads), params, L.smem_bytes, s->stream);
 	if (e != cudaSuccess) return e;
 	if (c.adaptive)
 	{
@@ -1482,18 +1617,19 @@ cudaError_t launch_pcg(mps_solver* s)
 	return cudaGetLastError();
 }
 
-template<int D>
+template<int D, bool MG>
 cudaError_t launch_pcg_dim(mps_solver* s)
 {
 	switch (s->cg.lanes_per_row)
 	{
-	case 1: return launch_pcg<1, D>(s);
-	case 2: return launch_pcg<2, D>(s);
-	case 4: return launch_pcg<4, D>(s);
-	default: return launch_pcg<8, D>(s);
+	case 1: return launch_pcg<1, D, MG>(s);
+	case 2: return launch_pcg<2, D, MG>(s);
+	case 4: return launch_pcg<4, D, MG>(s);
+	default: return launch_pcg<8, D, MG>(s);
 	}
 }
-cudaError_t launch_pcg_lpr(mps_solver* s) { return s->env.dim == 3 ? launch_pcg_dim<3>(s) : launch_pcg_dim<2>(s); }
+template<bool MG>
+cudaError_t launch_pcg_lpr(mps_solver* s) { return s->env.dim == 3 ? launch_pcg_dim<3, MG>(s) : launch_pcg_dim<2, MG>(s); }
 
 template<bool MG>
 cudaError_t launch_stream_lpr(mps_solver* s)
@@ -1551,11 +1687,9 @@ cudaError_t launch_lpr(mps_solver* s, CgArgs& args, unsigned want_blocks)
 
 } // namespace
 
-// the preconditioner needs the cell hierarchy of an assembled system; several GPUs still run the plain solve
-bool mg_active(const mps_solver* s)
-{
-	return s->mg.on && s->cg.chunked && !s->cg.external && !s->comm.on;
-}
+// the preconditioner needs the cell hierarchy of an assembled system; several ranks need each other's arenas mapped (peer memory)
+bool mg_wanted(const mps_solver* s) { return s->mg.on && s->cg.chunked && (!s->comm.on || s->comm.peer_mode == 1); }
+bool mg_active(const mps_solver* s) { return mg_wanted(s) && !s->cg.external; }
 
 cudaError_t launch_cg(mps_solver* s)
 {
@@ -1566,8 +1700,8 @@ cudaError_t launch_cg(mps_solver* s)
 		return cudaSuccess;
 	}
 	// multi-GPU: the persistent kernel coupled through peer memory when the ranks could map each other's arenas, else NCCL stepwise
+	if (mg_active(s)) return s->comm.on ? launch_pcg_lpr<true>(s) : launch_pcg_lpr<false>(s);
 	if (c.chunked && !c.external && s->comm.on) return (s->comm.peer_mode == 1) ? launch_stream_lpr<true>(s) : comm_cg_solve(s);
-	if (mg_active(s)) return launch_pcg_lpr(s);
 	if (c.chunked && !c.external) return launch_stream_lpr<false>(s);
 	CgArgs args;
 	args.n = c.n; args.rowptr = c.rowptr.p; args.col = c.col.p; args.val = c.val.p; args.b = c.b.p;

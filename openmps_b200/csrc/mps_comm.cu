@@ -38,6 +38,7 @@ struct Nccl
 	decltype(&ncclCommDestroy) CommDestroy = nullptr;
 	decltype(&ncclAllReduce) AllReduce = nullptr;
 	decltype(&ncclAllGather) AllGather = nullptr;
+	decltype(&ncclBroadcast) Broadcast = nullptr;
 	decltype(&ncclSend) Send = nullptr;
 	decltype(&ncclRecv) Recv = nullptr;
 	decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -56,7 +57,7 @@ struct Nccl
 		if (!lib) { error = std::string("cannot load libnccl: ") + dlerror(); return false; }
 #define MPS_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(lib, #sym)); if (!field) { error = "libnccl lacks " #sym; return false; }
 		MPS_SYM(GetUniqueId, ncclGetUniqueId) MPS_SYM(CommInitRank, ncclCommInitRank) MPS_SYM(CommDestroy, ncclCommDestroy)
-		MPS_SYM(AllReduce, ncclAllReduce) MPS_SYM(AllGather, ncclAllGather) MPS_SYM(Send, ncclSend) MPS_SYM(Recv, ncclRecv)
+		MPS_SYM(AllReduce, ncclAllReduce) MPS_SYM(AllGather, ncclAllGather) MPS_SYM(Broadcast, ncclBroadcast) MPS_SYM(Send, ncclSend) MPS_SYM(Recv, ncclRecv)
 		MPS_SYM(GroupStart, ncclGroupStart) MPS_SYM(GroupEnd, ncclGroupEnd) MPS_SYM(GetErrorString, ncclGetErrorString)
 #undef MPS_SYM
 		return true;
@@ -76,7 +77,8 @@ struct PeerGatherArgs
 	int rank, nranks, nfields;
 	unsigned long long* dst[4];
 	const unsigned long long* src[4][kMaxPeerRanks];
-	unsigned long long slab_words[4], total_words[4];
+	unsigned long long words_per_row[4];
+	unsigned long long begin[kMaxPeerRanks + 1]; // first row of every rank's slab
 };
 
 #define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
@@ -104,14 +106,7 @@ __global__ void k_halo_extent(const ChunkDesc* __restrict__ desc, const DevScala
 }
 
 struct Slab { uint64_t b, e; };
-inline Slab slab_of(const mps_solver* s, int rank)
-{
-	const uint64_t m = s->slab();
-	uint64_t b = static_cast<uint64_t>(rank) * m, e = b + m;
-	if (b > s->n) b = s->n;
-	if (e > s->n) e = s->n;
-	return Slab{ b, e };
-}
+inline Slab slab_of(const mps_solver* s, int rank) { return Slab{ s->slab_begin(rank), s->slab_begin(rank + 1) }; }
 
 // Halo extents of every rank (once per solve: the chunks were rebuilt by this step's assembly): ext[2k], ext[2k+1] = first /
 // one-past-last slot the windows of rank k reach.  One small all-gather + one host read-back.
@@ -134,8 +129,8 @@ cudaError_t halo_extents(mps_solver* s, std::vector<unsigned long long>& ext)
 	for (int k = 0; k < R; k++)
 	{
 		// a window must not reach past the adjacent slab (slabs thinner than one cell column are not supported)
-		const uint64_t lo_ok = (k > 0) ? static_cast<uint64_t>(k - 1) * s->slab() : 0;
-		const uint64_t hi_ok = (k + 1 < R) ? std::min<uint64_t>(static_cast<uint64_t>(k + 2) * s->slab(), s->n) : s->n;
+		const uint64_t lo_ok = (k > 0) ? s->slab_begin(k - 1) : 0;
+		const uint64_t hi_ok = (k + 1 < R) ? s->slab_begin(k + 2) : s->n;
 		if (ext[2 * k] < lo_ok || ext[2 * k + 1] > hi_ok + 1 /* window ends are rounded up to even */) { s->comm_error = "slab thinner than the neighbour stencil: use fewer GPUs for this problem"; return cudaErrorUnknown; }
 	}
 	return cudaSuccess;
@@ -174,7 +169,8 @@ cudaError_t halo_exchange(mps_solver* s, double* z, const std::vector<unsigned l
 // ---- peer-memory coupling of the persistent CG kernel ----------------------------------------------------------------------
 namespace {
 
-inline size_t arena_size(uint64_t rows) { return kPeerHeaderBytes + 2ull * rows * sizeof(double2); }
+inline size_t arena_mg_offset(uint64_t rows) { return kPeerHeaderBytes + 2ull * rows * sizeof(double2); } // [header | z0 | z1 | mg]
+inline size_t arena_size(uint64_t rows, uint64_t mg_doubles) { return arena_mg_offset(rows) + mg_doubles * sizeof(double); }
 
 bool allocation_offset(void* p, unsigned long long* offset);
 
@@ -252,7 +248,7 @@ void comm_release_peers(mps_solver* s)
 	close_peers(s);
 	if (c.on && c.peer_mode == 1) comm_barrier(s); // nobody frees memory a peer still maps
 	cudaFree(c.arena);
-	c.arena = nullptr; c.arena_bytes = 0; c.arena_rows = 0;
+	c.arena = nullptr; c.arena_bytes = 0; c.arena_rows = 0; c.arena_mg = 0;
 	if (s->cg.z_borrowed) { s->cg.z0.p = nullptr; s->cg.z0.cap = 0; s->cg.z1.p = nullptr; s->cg.z1.cap = 0; s->cg.z_borrowed = false; }
 }
 
@@ -261,31 +257,33 @@ void comm_release_peers(mps_solver* s)
 // re-allocated — every rank holds the same particles, so all of them take this branch in the same step.  IPC handles travel
 // through an NCCL all-gather of a small device buffer; peers map them with cudaIpcOpenMemHandle (which enables peer access).
 // If any rank cannot export or map (no P2P, IPC disabled in the container) all ranks agree on the NCCL paths.
-cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows)
+cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows, uint64_t mg_doubles)
 {
 	Comm& c = s->comm;
 	CgBuffers& cg = s->cg;
 	cudaStream_t st = s->stream;
 	const void* now[8];
 	state_pointers(s, now);
-	bool same = c.arena && rows <= c.arena_rows;
+	bool same = c.arena && rows <= c.arena_rows && mg_doubles <= c.arena_mg;
 	for (int f = 0; f < 8 && same; f++) same = (now[f] == c.exported[f]);
 	if (same) return cudaSuccess;
 	const int R = c.nranks;
-	const bool regrow = !c.arena || rows > c.arena_rows;
+	const bool regrow = !c.arena || rows > c.arena_rows || mg_doubles > c.arena_mg;
+	const uint64_t old_rows = c.arena_rows, old_mg = c.arena_mg; // a regrown arena never shrinks either section
 	MPS_TRY(cudaStreamSynchronize(st));
 	if (c.arena && regrow) comm_release_peers(s);
 	else if (c.arena) { close_peers(s); if (c.peer_mode == 1) MPS_TRY(comm_barrier(s)); }
 	if (regrow)
 	{
 		if (!cg.z_borrowed) { cg.z0.release(); cg.z1.release(); }
-		const uint64_t want_rows = rows + rows / 4 + 16;
-		size_t bytes = arena_size(want_rows);
+		const uint64_t want_rows = std::max<uint64_t>(rows + rows / 4 + 16, old_rows);
+		const uint64_t want_mg = std::max<uint64_t>(mg_doubles ? mg_doubles + mg_doubles / 4 + 64 : 0, old_mg);
+		size_t bytes = arena_size(want_rows, want_mg);
 		bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
 		void* mem = nullptr;
 		MPS_TRY(cudaMalloc(&mem, bytes));
 		MPS_TRY(cudaMemsetAsync(mem, 0, bytes, st));
-		c.arena = static_cast<unsigned char*>(mem); c.arena_bytes = bytes; c.arena_rows = want_rows;
+		c.arena = static_cast<unsigned char*>(mem); c.arena_bytes = bytes; c.arena_rows = want_rows; c.arena_mg = want_mg;
 		cg.z0.p = reinterpret_cast<double*>(c.arena + kPeerHeaderBytes); cg.z0.cap = 2 * want_rows;
 		cg.z1.p = cg.z0.p + 2 * want_rows; cg.z1.cap = 2 * want_rows;
 		cg.z_borrowed = true;
@@ -387,14 +385,12 @@ __global__ void __launch_bounds__(256) k_peer_gather(PeerGatherArgs a)
 	const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
 	for (int f = 0; f < a.nfields; f++)
 	{
-		const unsigned long long slab = a.slab_words[f], total = a.total_words[f];
+		const unsigned long long w = a.words_per_row[f];
 		unsigned long long* __restrict__ dst = a.dst[f];
 		for (int r = 0; r < a.nranks; r++)
 		{
 			if (r == a.rank) continue;
-			const unsigned long long b = static_cast<unsigned long long>(r) * slab;
-			unsigned long long e = b + slab;
-			if (e > total) e = total;
+			const unsigned long long b = a.begin[r] * w, e = a.begin[r + 1] * w;
 			const unsigned long long* __restrict__ src = a.src[f][r];
 			for (unsigned long long i = b + tid; i < e; i += nthreads) dst[i] = src[i];
 		}
@@ -421,7 +417,6 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 {
 	if (!s->comm.on || s->n == 0) return cudaSuccess;
 	Comm& c = s->comm;
-	const uint64_t m = s->slab();
 	const int vs = s->vec_stride();
 	const int k = c.rank;
 	MPS_TRY(comm_ensure_arena(s, s->n + 64)); // first use (or re-allocated state): exchange the IPC handles
@@ -434,8 +429,9 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 			const int f = 2 * field + s->cur, q = a.nfields++;
 			a.dst[q] = reinterpret_cast<unsigned long long*>(c.peer_state[k][f]);
 			for (int r = 0; r < c.nranks; r++) a.src[q][r] = reinterpret_cast<const unsigned long long*>(c.peer_state[r][f]);
-			a.slab_words[q] = m * words_per_row; a.total_words[q] = s->n * words_per_row;
+			a.words_per_row[q] = words_per_row;
 		};
+		for (int r = 0; r <= c.nranks; r++) a.begin[r] = s->slab_begin(r);
 		if (pos) add(0, vs);
 		if (vel) add(1, vs);
 		if (prs) add(2, 1);
@@ -448,11 +444,38 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 		c.peer_gathers += 1;
 		return cudaGetLastError();
 	}
-	if (pos) { double* p = s->pos[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
-	if (vel) { double* p = s->vel[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m * vs, p, m * vs, ncclDouble, comm_of(s), s->stream)); }
-	if (prs) { double* p = s->prs[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
-	if (nden) { double* p = s->nden[s->cur].p; MPS_NCCL(s, g_nccl.AllGather(p + static_cast<uint64_t>(k) * m, p, m, ncclDouble, comm_of(s), s->stream)); }
+	// slabs are uneven (cell-column aligned): every rank broadcasts its slab, one group per field
+	auto gather = [&](double* p, uint64_t w) -> cudaError_t
+	{
+		MPS_NCCL(s, g_nccl.GroupStart());
+		for (int r = 0; r < c.nranks; r++)
+		{
+			const uint64_t b = s->slab_begin(r), e = s->slab_begin(r + 1);
+			if (e > b) MPS_NCCL(s, g_nccl.Broadcast(p + b * w, p + b * w, (e - b) * w, ncclDouble, r, comm_of(s), s->stream));
+		}
+		MPS_NCCL(s, g_nccl.GroupEnd());
+		return cudaSuccess;
+	};
+	if (pos) MPS_TRY(gather(s->pos[s->cur].p, vs));
+	if (vel) MPS_TRY(gather(s->vel[s->cur].p, vs));
+	if (prs) MPS_TRY(gather(s->prs[s->cur].p, 1));
+	if (nden) MPS_TRY(gather(s->nden[s->cur].p, 1));
 	s->stats.comm_calls += (pos ? 1 : 0) + (vel ? 1 : 0) + (prs ? 1 : 0) + (nden ? 1 : 0);
+	return cudaSuccess;
+}
+
+double* comm_mg_section(mps_solver* s, int rank)
+{
+	Comm& c = s->comm;
+	if (!c.peer_arena[rank]) return nullptr;
+	return reinterpret_cast<double*>(c.peer_arena[rank] + arena_mg_offset(c.arena_rows));
+}
+
+cudaError_t comm_allreduce_sum(mps_solver* s, double* p, uint64_t count)
+{
+	if (!s->comm.on || count == 0) return cudaSuccess;
+	MPS_NCCL(s, g_nccl.AllReduce(p, p, count, ncclDouble, ncclSum, comm_of(s), s->stream));
+	s->stats.comm_calls += 1;
 	return cudaSuccess;
 }
 
@@ -556,7 +579,6 @@ int mps_comm_init(mps_handle s, int rank, int nranks, const void* id128)
 	const ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
 	if (r != ncclSuccess) { s->last_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return MPS_NCCL_ERROR; }
 	s->comm.nccl = comm; s->comm.rank = rank; s->comm.nranks = nranks; s->comm.on = true;
-	s->mg.on = false; // the cell hierarchy of the preconditioner is single-GPU for now: several ranks run the plain solve
 	return MPS_OK;
 }
 

@@ -140,6 +140,7 @@ struct PeerLink
 // ---- multigrid preconditioner on the cell hierarchy (mps_mg.cu builds it, mps_cg.cu k_pcg_stream applies it) --------------
 constexpr uint32_t kMgNone = 0xffffffffu;
 constexpr int kMgMaxLevels = 16;
+constexpr int kMgMaxDistLevels = 3;  // multi-GPU: at most this many leading levels are distributed over the ranks (slab alignment 2^3 columns)
 struct MgLevelPtrs
 {
 	const uint64_t* count;   // occupied cells of this level (device value: the total of the level's rank scan)
@@ -151,6 +152,24 @@ struct MgLevelPtrs
 	double* r;               // [cells] restricted residual
 	double* e0;              // [cells] correction, two buffers (Jacobi sweeps ping-pong)
 	double* e1;
+	// multi-GPU: dense index -> compact id (the level's rank scan, dense + 1 entries), cells per x column, and where the level's
+	// vectors sit inside the "mg" section of every rank's peer arena (doubles)
+	const uint64_t* ranktab;
+	uint64_t colstride, dense;
+	uint64_t off_r, off_e0, off_e1;
+};
+// Several ranks (mps_comm.cu, DESIGN.md "multi-GPU"): slabs are cut on cell columns that are multiples of 2^k, so every cell of
+// levels 0 .. k belongs to exactly one rank and a rank's cells are one contiguous range of compact ids at each of those levels.
+// Levels [0, k) are DISTRIBUTED: a rank smooths / restricts / prolongs its own cells and reads the neighbour ranks' halo cells
+// straight from their arenas over NVLink; level k is GATHERED (every rank pulls the other ranks' cells) and levels >= k are
+// replicated: every rank runs them whole, on identical data, with identical results.  k = 0: the whole cycle is replicated.
+struct MgDist
+{
+	int on;                                // 0 on one GPU
+	int k;
+	int rank, nranks;
+	uint32_t col_b[kMaxPeerRanks + 1];     // first level-0 cell column of every rank's slab
+	double* peer_vec[kMaxPeerRanks];       // the mg section of every rank's arena ([rank] is local)
 };
 struct MgArgs
 {
@@ -163,6 +182,7 @@ struct MgArgs
 	const double* dinv0;     // [rows] 1 / a_ii (0 for rows without entries)
 	double* r;               // [rows] residual
 	MgLevelPtrs lv[kMgMaxLevels];
+	MgDist dist;
 };
 
 template<int D>

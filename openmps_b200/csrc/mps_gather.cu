@@ -733,7 +733,7 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 	// the streaming kernel stages even-aligned windows: one element of slack behind every vector
 	MPS_TRY(cg.b.ensure(n + 64, st)); MPS_TRY(cg.x.ensure(n + 64, st)); if (!cg.chunked) MPS_TRY(cg.r.ensure(n + 64, st));
 	MPS_TRY(cg.ap.ensure(n + 64, st));
-	const bool pre_on = s->mg.on && cg.chunked && !s->comm.on; // == mg_active(s) once cg.external is reset below
+	const bool pre_on = mg_wanted(s); // == mg_active(s) once cg.external is reset below
 	if (pre_on) MPS_TRY(cg.r.ensure(n + 64, st));
 	if (cg.chunked && s->comm.on) MPS_TRY(comm_ensure_arena(s, n + 64)); // {r, p} live in the arena the neighbour ranks map
 	else if (cg.chunked) { MPS_TRY(cg.z0.ensure(2 * (n + 64), st)); MPS_TRY(cg.z1.ensure(2 * (n + 64), st)); }

@@ -15,6 +15,9 @@
 //   scan          C x 12 B
 //   k_scatter     N x 16 B ; k_rank_fix N x (4 + occupancy x 4) ; k_reorder N x 2 x (16D + 16 + 1 + 4 + 4)
 //   k_search<false/true>  N x (pos of ~3^D cells from L1/L2) -> counts / list
+#include <cstdlib>
+#include <vector>
+
 #include "mps_solver.h"
 
 namespace mps {
@@ -191,6 +194,50 @@ __global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n,
 	if (!FILL) nbr_cnt[i] = cnt;
 }
 
+// Multi-GPU: slab boundaries of this step.  The nominal split is equal counts of the slots that lie in the grid; every boundary
+// then moves up to the next boundary between cell COLUMNS (all cells of one x index) whose index is a multiple of 2^a, so that
+// cells — and the 2^a-column blocks of the preconditioner's first a levels — are never shared between ranks.  a is the largest
+// value <= a_max for which every rank still gets at least one block of columns; out = [R + 1 slots | R + 1 columns | a | ok].
+// The Disabled tail (slots behind the grid) goes to the last rank.  One thread: R binary searches over the cell table.
+__global__ void k_slab_bounds(const int R, const uint64_t n, const uint64_t ncells, const uint32_t ncols, const uint64_t colstride, const int a_max,
+	const uint64_t* __restrict__ cell_start, unsigned long long* __restrict__ out)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	const uint64_t in_grid = cell_start[ncells];
+	int a = a_max;
+	bool ok = false;
+	for (; a >= 0 && !ok; a--)
+	{
+		const uint32_t unit = 1u << a, units = (ncols + unit - 1) / unit;
+		ok = true;
+		uint32_t prev = 0;
+		for (int r = 0; r <= R; r++)
+		{
+			uint32_t col; uint64_t slot;
+			if (r == 0) { col = 0; slot = 0; }
+			else if (r == R) { col = units * unit; slot = n; }
+			else
+			{
+				const uint64_t target = in_grid / R * r + in_grid % R * r / R;
+				uint32_t lo = 0, hi = units; // smallest block of columns whose first slot is >= target
+				while (lo < hi)
+				{
+					const uint32_t mid = (lo + hi) >> 1;
+					const uint64_t c = static_cast<uint64_t>(mid) * unit;
+					if (cell_start[(c < ncols ? c : ncols) * colstride] < target) lo = mid + 1; else hi = mid;
+				}
+				col = lo * unit;
+				slot = cell_start[(col < ncols ? col : ncols) * colstride];
+			}
+			if (r > 0 && col <= prev) ok = false;
+			prev = col;
+			out[r] = slot; out[R + 1 + r] = col;
+		}
+		if (ok) { out[2 * R + 2] = static_cast<unsigned long long>(a); break; }
+	}
+	out[2 * R + 3] = ok ? 1ull : 0ull;
+}
+
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_get_cells(uint64_t n, const Vec<D>* __restrict__ pos, const uint32_t* __restrict__ orig,
 	long long* __restrict__ out, EnvConst env)
@@ -251,6 +298,26 @@ cudaError_t sort_and_search(mps_solver* s)
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->cell_count.p, s->cell_start.p, env.ncells + 1, s->scan_tmp, st, &s->stats.kernel_launches));
 	// 2b. occupied cells -> compact ids: level 0 of the multigrid preconditioner's cell hierarchy (mps_mg.cu)
 	MPS_TRY(launch_mg_rank0(s));
+	// 2c. multi-GPU: this step's slab boundaries, on cell columns (one extra, tiny host round trip per step)
+	if (s->comm.on)
+	{
+		const int R = s->comm.nranks;
+		MPS_TRY(s->d_bounds.ensure(2ull * R + 4, st));
+		const uint64_t colstride = env.ncells / static_cast<uint64_t>(env.grid_n[0]);
+		int a_max = s->mg.on ? kMgMaxDistLevels : 0;
+		if (const char* v = std::getenv("MPS_SLAB_ALIGN")) { const int k = std::atoi(v); if (k >= 0 && k <= kMgMaxDistLevels) a_max = k; }
+		k_slab_bounds<<<1, 32, 0, st>>>(R, n, env.ncells, static_cast<uint32_t>(env.grid_n[0]), colstride, a_max, s->cell_start.p, s->d_bounds.p);
+		s->stats.kernel_launches += 1;
+		std::vector<unsigned long long> hb(2ull * R + 4);
+		MPS_TRY(cudaMemcpyAsync(hb.data(), s->d_bounds.p, hb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		MPS_TRY(cudaStreamSynchronize(st));
+		if (!hb[2 * R + 3]) { s->comm_error = "fewer cell columns than GPUs: use fewer GPUs for this problem"; return cudaErrorUnknown; }
+		s->own_b.assign(hb.begin(), hb.begin() + R + 1);
+		s->col_b.resize(R + 1);
+		for (int r = 0; r <= R; r++) s->col_b[r] = static_cast<uint32_t>(hb[R + 1 + r]);
+		s->slab_align = static_cast<int>(hb[2 * R + 2]);
+		s->own_n = n;
+	}
 	// 3. scatter, deterministic order inside each cell, permute the state
 	k_scatter<<<nb, kThreads, 0, st>>>(n, s->key.p, s->rank.p, s->cell_start.p, cur.orig, s->perm.p, s->perm_orig.p);
 	k_rank_fix<<<nb, kThreads, 0, st>>>(n, static_cast<uint32_t>(env.ncells), s->key.p, s->cell_start.p, s->perm.p, s->perm_orig.p, s->perm2.p);

@@ -214,6 +214,28 @@ __global__ void __launch_bounds__(kThreads) k_mg_galerkin(uint64_t bound, const 
 	dinv_hi[C] = (acc[K / 2] != 0.0) ? omega / acc[K / 2] : 0.0;
 }
 
+// several ranks: before level k's operator is summed over the ranks, everything outside this rank's own cells becomes zero
+// (x + 0 is exact in any order: every rank ends up with bit-identical stencils)
+__global__ void __launch_bounds__(kThreads) k_mg_mask(uint64_t bound, int K, const uint64_t* __restrict__ ranktab, uint64_t colstride, uint64_t dense, int level,
+	uint32_t col_lo, uint32_t col_hi, double* __restrict__ S)
+{
+	const uint64_t t = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	if (t >= bound * K) return;
+	uint64_t ilo = static_cast<uint64_t>(col_lo >> level) * colstride, ihi = static_cast<uint64_t>(col_hi >> level) * colstride;
+	if (ilo > dense) ilo = dense;
+	if (ihi > dense) ihi = dense;
+	const uint64_t lo = ranktab[ilo], hi = ranktab[ihi];
+	const uint64_t c = t / K;
+	if (c < lo || c >= hi) S[t] = 0.0;
+}
+__global__ void __launch_bounds__(kThreads) k_mg_dinv(uint64_t bound, int K, const double* __restrict__ S, double* __restrict__ dinv, double omega)
+{
+	const uint64_t c = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	if (c >= bound) return;
+	const double d = S[c * K + K / 2];
+	dinv[c] = (d != 0.0) ? omega / d : 0.0;
+}
+
 #define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
 
 Dims dims_of(const MgLevelBufs& l) { Dims d; for (int a = 0; a < 3; a++) d.n[a] = l.dims[a]; return d; }
@@ -267,9 +289,23 @@ cudaError_t setup(mps_solver* s)
 	k_mg_s0<D><<<blocks_for(l0.bound * K, kThreads), kThreads, 0, st>>>(l0.bound, l0.rank.p + l0.dense, mg.cstart.p, s->row_len.p, mg.row_s.p, n, l0.S.p,
 		l0.dinv.p, mg.omega);
 	L += 1;
-	for (int l = 0; l + 1 < mg.levels; l++)
+	for (int l = 0; l < mg.levels; l++)
 	{
-		MgLevelBufs& lo = mg.lv[l]; MgLevelBufs& hi = mg.lv[l + 1];
+		MgLevelBufs& lo = mg.lv[l];
+		if (s->comm.on && l == mg.k_dist)
+		{
+			// Several ranks: up to here every rank holds the operators of its own cells only (its rows, its children).  Level k is
+			// summed over the ranks (exact: one non-zero contribution per entry) and everything above is rebuilt from it, whole and
+			// identical on every rank.
+			const uint64_t colstride = lo.dense / static_cast<uint64_t>(lo.dims[0]);
+			k_mg_mask<<<blocks_for(lo.bound * K, kThreads), kThreads, 0, st>>>(lo.bound, K, lo.rank.p, colstride, lo.dense, l, s->col_b[s->comm.rank],
+				s->col_b[s->comm.rank + 1], lo.S.p);
+			MPS_TRY(comm_allreduce_sum(s, lo.S.p, lo.bound * K));
+			k_mg_dinv<<<blocks_for(lo.bound, kThreads), kThreads, 0, st>>>(lo.bound, K, lo.S.p, lo.dinv.p, mg.omega);
+			L += 2;
+		}
+		if (l + 1 == mg.levels) break;
+		MgLevelBufs& hi = mg.lv[l + 1];
 		k_mg_galerkin<D><<<blocks_for(hi.bound, kThreads), kThreads, 0, st>>>(hi.bound, hi.rank.p + hi.dense, dims_of(lo), lo.key.p, hi.child.p, lo.nbr.p, lo.S.p,
 			hi.S.p, hi.dinv.p, mg.omega);
 		L += 1;
@@ -292,6 +328,7 @@ void mg_configure(mps_solver* s)
 	if (const char* v = std::getenv("MPS_MG_GAMMA")) mg.gamma = std::atof(v);
 	if (const char* v = std::getenv("MPS_MG_TOP_SWEEPS")) { const int k = std::atoi(v); if (k >= 0 && k <= 64) mg.top_sweeps = k; }
 	if (const char* v = std::getenv("MPS_MG_TOP_CELLS")) { const int k = std::atoi(v); if (k >= 1) mg.top_cells = static_cast<uint32_t>(k); }
+	if (const char* v = std::getenv("MPS_MG_DIST_CELLS")) { const long long k = std::atoll(v); if (k >= 0) mg.dist_cells = static_cast<uint64_t>(k); }
 	long long d[3] = { 1, 1, 1 };
 	for (int a = 0; a < D; a++) d[a] = s->env.grid_n[a];
 	int l = 0;
@@ -331,7 +368,9 @@ cudaError_t mg_ensure(mps_solver* s, uint64_t cells0)
 	const int K = (s->env.dim == 3) ? 27 : 9, CH = 1 << s->env.dim;
 	cudaStream_t st = s->stream;
 	mg.cells0 = cells0;
+	mg.in_arena = s->comm.on;
 	uint64_t bound = cells0;
+	uint64_t off = 0;
 	for (int l = 0; l < mg.levels; l++)
 	{
 		MgLevelBufs& lv = mg.lv[l];
@@ -342,7 +381,21 @@ cudaError_t mg_ensure(mps_solver* s, uint64_t cells0)
 		MPS_TRY(lv.key.ensure(bound, st)); MPS_TRY(lv.nbr.ensure(bound * K, st)); MPS_TRY(lv.parent.ensure(bound, st));
 		if (l > 0) MPS_TRY(lv.child.ensure(bound * CH, st));
 		MPS_TRY(lv.S.ensure(bound * K, st)); MPS_TRY(lv.dinv.ensure(bound, st));
-		MPS_TRY(lv.r.ensure(bound, st)); MPS_TRY(lv.e0.ensure(bound, st)); MPS_TRY(lv.e1.ensure(bound, st));
+		if (!mg.in_arena) { MPS_TRY(lv.r.ensure(bound, st)); MPS_TRY(lv.e0.ensure(bound, st)); MPS_TRY(lv.e1.ensure(bound, st)); }
+		const uint64_t pad = (bound + 1) & ~1ull;
+		for (int q = 0; q < 3; q++) { mg.vec_off[l][q] = off; off += pad; }
+	}
+	mg.vec_total = off;
+	if (mg.in_arena)
+	{
+		// several ranks: the level vectors live in the peer arena, at the same offsets on every rank (the bounds follow from cells0,
+		// which every rank computes from the same replicated state).  Which levels are distributed: those estimated (cells0 / 2^(D l))
+		// to hold more than dist_cells cells, at most as many as the slab alignment of this step allows.
+		MPS_TRY(comm_ensure_arena(s, s->n + 64, mg.vec_total));
+		int k = 0;
+		uint64_t est = cells0;
+		while (k < s->slab_align && k < kMgMaxDistLevels && k + 1 < mg.levels && est > mg.dist_cells) { k++; est >>= s->env.dim; }
+		mg.k_dist = k;
 	}
 	MPS_TRY(mg.crow.ensure(s->n + 64, st)); MPS_TRY(mg.cstart.ensure(cells0 + 2, st));
 	MPS_TRY(mg.dinv0.ensure(s->n + 64, st));

@@ -109,6 +109,13 @@ struct MgBuffers
 	DevBuf<uint32_t> crow;
 	DevBuf<uint64_t> cstart;
 	DevBuf<double> dinv0, row_s;
+	// several ranks: the level vectors r / e0 / e1 live in the "mg" section of the peer arena (same layout on every rank) so that
+	// neighbour ranks can read halo cells; MgLevelBufs::r / e0 / e1 are then unused
+	bool in_arena = false;
+	int k_dist = 0;                  // levels [0, k_dist) distributed, level k_dist gathered, the rest replicated (MgDist)
+	uint64_t dist_cells = 150000;    // a level is distributed when it is estimated to hold more cells than this (MPS_MG_DIST_CELLS)
+	uint64_t vec_off[kMgMaxLevels][3] = {}; // r, e0, e1 of each level inside the mg section (doubles)
+	uint64_t vec_total = 0;
 };
 
 } // namespace mps
@@ -128,6 +135,7 @@ struct Comm
 	unsigned char* arena = nullptr;    // this rank's arena
 	size_t arena_bytes = 0;
 	uint64_t arena_rows = 0;           // rows the z sections are sized for
+	uint64_t arena_mg = 0;             // doubles of the mg section behind them (level vectors of the preconditioner)
 	unsigned char* peer_arena[8] = {}; // peers' arenas mapped into this process ([rank] = arena)
 	void* peer_base[8] = {};           // what cudaIpcOpenMemHandle returned (to close)
 	unsigned long long solves = 0;     // persistent solves so far (tag of the mailbox flags)
@@ -205,11 +213,21 @@ struct mps_solver
 
 	int vec_stride() const { return env.dim == 2 ? 2 : 4; }
 
-	// multi-GPU: rows (slots) this rank computes; the state itself is replicated (DESIGN.md "multi-GPU")
+	// multi-GPU: rows (slots) this rank computes; the state itself is replicated (DESIGN.md "multi-GPU").  The nominal split is
+	// equal slot counts (mps_partition_range); every sort then moves the boundaries to the nearest boundary between cell COLUMNS
+	// (all cells of one x index; a multiple of 2^slab_align columns) so that every cell — and every block of the preconditioner's
+	// first slab_align levels — belongs to exactly one rank (mps_grid.cu k_slab_bounds).
 	mps::Comm comm;
-	uint64_t slab() const { return comm.on ? (n + comm.nranks - 1) / comm.nranks : n; }
-	uint64_t own0() const { const uint64_t b = static_cast<uint64_t>(comm.rank) * slab(); return comm.on ? (b < n ? b : n) : 0; }
-	uint64_t own1() const { const uint64_t e = static_cast<uint64_t>(comm.rank + 1) * slab(); return comm.on ? (e < n ? e : n) : n; }
+	std::vector<uint64_t> own_b;           // [nranks + 1] first slot of every rank's slab (valid while own_n == n)
+	std::vector<uint32_t> col_b;           // [nranks + 1] first cell column of every rank's slab
+	uint64_t own_n = ~0ull;
+	int slab_align = 0;                    // slab boundaries are multiples of 2^slab_align cell columns
+	mps::DevBuf<unsigned long long> d_bounds; // device scratch of k_slab_bounds: [own_b | col_b]
+	bool slabs_set() const { return comm.on && own_n == n && own_b.size() == static_cast<size_t>(comm.nranks) + 1; }
+	uint64_t nominal(int r) const { const uint64_t m = (n + comm.nranks - 1) / comm.nranks, b = static_cast<uint64_t>(r) * m; return b < n ? b : n; }
+	uint64_t slab_begin(int r) const { return slabs_set() ? own_b[r] : nominal(r); }
+	uint64_t own0() const { return comm.on ? slab_begin(comm.rank) : 0; }
+	uint64_t own1() const { return comm.on ? slab_begin(comm.rank + 1) : n; }
 };
 
 namespace mps {
@@ -239,7 +257,9 @@ cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
 // mps_comm.cu
 cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden = false); // no-op without a communicator
 cudaError_t comm_cg_solve(mps_solver* s);                                       // multi-rank CG (stepwise kernels + NCCL)
-cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows);                    // (re)allocates + exchanges the peer arenas; sets cg.z0 / cg.z1
+cudaError_t comm_ensure_arena(mps_solver* s, uint64_t rows, uint64_t mg_doubles = 0); // (re)allocates + exchanges the peer arenas; sets cg.z0 / cg.z1
+cudaError_t comm_allreduce_sum(mps_solver* s, double* p, uint64_t count);       // in place, NCCL, on the solver's stream
+double* comm_mg_section(mps_solver* s, int rank);                               // the mg section of `rank`'s arena as mapped here
 cudaError_t comm_prepare_link(mps_solver* s);                                   // halo extents -> comm.link for the next persistent solve
 void comm_release_peers(mps_solver* s);
 // mps_scan.cu
@@ -252,7 +272,8 @@ void mg_configure(mps_solver* s);                       // level geometry from t
 cudaError_t launch_mg_rank0(mps_solver* s);             // during the sort: occupied cells -> compact ids
 cudaError_t mg_ensure(mps_solver* s, uint64_t cells0);  // sizes every level for `cells0` occupied cells
 cudaError_t launch_mg_setup(mps_solver* s);             // after k_ppe_fill: topology + Galerkin operators of every level
-bool mg_active(const mps_solver* s);                    // this solve is preconditioned (single GPU, chunked, switch on)
+bool mg_wanted(const mps_solver* s);                    // the next assembly should build the hierarchy (as mg_active, before cg.external is reset)
+bool mg_active(const mps_solver* s);                    // this solve is preconditioned (chunked, switch on, peer memory if several ranks)
 // mps_cg.cu
 cudaError_t cg_configure(mps_solver* s);                // picks chunk limits / pipeline depth for this environment
 cudaError_t launch_cg(mps_solver* s);

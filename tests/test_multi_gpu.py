@@ -82,7 +82,9 @@ def test_two_gpus_match_one_gpu(scene, steps, coupling):
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     env = dict(os.environ)
     if coupling == "nccl":
+        # the NCCL coupling runs the reference's plain CG between per-phase launches: the one-GPU run it is compared with does too
         env["MPS_COMM_NCCL_ONLY"] = "1"
+        env["MPS_CG_PRECOND"] = "0"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29612", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), scene, str(steps)],
                        capture_output=True, text=True, timeout=900, env=env)

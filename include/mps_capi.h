@@ -104,6 +104,21 @@ int mps_upload(mps_handle h, const double* x, const double* u, const double* p, 
  * the coming steps.  The C++ drop-in evaluates the user's callable on the host and forwards the result here. */
 int mps_set_wall_positions(mps_handle h, uint64_t n, const uint64_t* ids, const double* x);
 
+/* positionWall(i, t, dt) evaluated ON THE DEVICE for analytic motions (pistons, shaking tanks): no host callback and no upload per
+ * step.  The listed particles (ids == NULL: every non-fluid particle) follow, from the next step on,
+ *     x(t) = base + velocity * tau + amplitude * (sin(omega * tau + phase) - sin(phase)),  tau = clamp(t - t_begin, 0, t_end - t_begin)
+ * where base is the position they were added with (or last given through mps_set_wall_positions) and t is Environment::T() of the
+ * step, exactly the t the reference hands to its callback (Computer.hpp:921,1015).  2-D: components are {x, z}.  Up to 8 motions per
+ * handle; motion == NULL removes all of them. */
+typedef struct mps_wall_motion
+{
+	double amplitude[3];
+	double velocity[3];
+	double omega, phase;
+	double t_begin, t_end;
+} mps_wall_motion;
+int mps_set_wall_motion(mps_handle h, uint64_t n, const uint64_t* ids, const mps_wall_motion* motion);
+
 /* ---- time stepping (the hot path) --------------------------------------------------------------------------------- */
 int mps_determine_dt(mps_handle h, double* dt);           /* replaces Computer::DetermineDt, Computer.hpp:759-777 */
 int mps_forward_time(mps_handle h, double dt);            /* replaces Computer::ForwardTime(dt), Computer.hpp:1700-1742 */
@@ -149,6 +164,37 @@ int mps_get_solution(mps_handle h, uint64_t n, double* x);
  * 6 r, 7 e0, 8 e1 (f64); level = -1: 0 row -> cell (u32 x n), 1 first row of every cell (u64 x cells + 1), 2 1 / a_ii (f64 x n),
  * 3 slot -> original particle id (u32 x n).  *count = elements available; at most capacity_bytes are copied to out. */
 int mps_debug_mg(mps_handle h, int level, int which, void* out, uint64_t capacity_bytes, uint64_t* count);
+
+/* ---- benchmark observables as device reductions ------------------------------------------------------------------------
+ * The reference's plotting scripts re-read result/particles_%05d.csv to get these; here ONE pass over the resident state on the
+ * GPU returns them (24 doubles instead of a 52 B/particle download), so that long-run physical parity is an assertion:
+ *   edge_x                      Benchmark/DamBreak/koshizukaoka1996_edge.py:14-20   max x over Type 0 (leading edge of the collapse)
+ *   h1, h2, p2_sum / p2_count   Benchmark/DamBreak/zhouetal1999.py:26-39            water height at x_h1 / x_h2 (highest particle with
+ *                                                                                  n > min_n within l0/2), mean p of Wall particles with x < 0
+ *                                                                                  within d/2 of z_p2
+ *   r_min/r_max_surface, center_p  Benchmark/CentralGravity/check_result.py:26-57   extremes of |x| over particles with n < surface_n
+ *                                                                                  (= beta n0), p of the particle nearest the origin
+ *   inner, sum_d, sum_p, sum_dd, sum_dp, max_dev   hydrostatic column (Benchmark/StaticPressure): moments of (depth = surface_z - z, p)
+ *                                                                                  over Fluid with p > 0 and max |p - rho_g depth|
+ * Counts are exact integers carried as doubles.  Fields whose set is empty hold -DBL_MAX (maxima) / DBL_MAX (minima). */
+typedef struct mps_observe_params
+{
+	double surface_n;   /* central gravity: n below this marks a surface particle */
+	double rho_g;       /* hydrostatic reference gradient rho * g */
+	double surface_z;   /* z of the free surface (depth = surface_z - z); use top_z of an earlier call if unknown */
+	double x_h1, x_h2, min_n, z_p2, d; /* Zhou et al. probe stations */
+} mps_observe_params;
+typedef struct mps_observables
+{
+	double edge_x, top_z;
+	double r_max_surface, r_min_surface;
+	double center_r2, center_id, center_p;
+	double inner, sum_d, sum_p, sum_dd, sum_dp, max_dev;
+	double h1, h2, p2_sum, p2_count;
+	double fluid, wall, dummy, disabled;
+	double p_max, u_max2, surface_count;
+} mps_observables;
+int mps_observe(mps_handle h, const mps_observe_params* params, mps_observables* out);
 
 /* ---- multi-GPU (no counterpart in the reference, which is single-process OpenMP) ------------------------------------
  * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,

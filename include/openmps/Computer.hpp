@@ -484,6 +484,20 @@ namespace { namespace OpenMps
 			return static_cast<std::size_t>(steps);
 		}
 
+		// Wall motion without the host in the loop: the listed non-fluid particles (empty list: all of them) follow
+		//   positionWall(i, t, dt) + velocity * tau + amplitude * (sin(omega * tau + phase) - sin(phase)),  tau = clamp(t - t_begin, 0, t_end - t_begin)
+		// evaluated on the device inside the explicit stage (mps_set_wall_motion), with the positionWall callable giving the base
+		// position as before.  With it RunUntil() also serves pistons and shaking tanks (the reference evaluates the callable for
+		// every non-fluid particle in every step, :993, :1012-1019).
+		void SetWallMotion(const std::vector<std::uint64_t>& ids, const mps_wall_motion& motion)
+		{
+			Check(mps_set_wall_motion(device.h, ids.size(), ids.empty() ? nullptr : ids.data(), &motion));
+		}
+		void ClearWallMotion()
+		{
+			Check(mps_set_wall_motion(device.h, 0, nullptr, nullptr));
+		}
+
 		// append particles (reference :1754-1777)
 		template<typename PARTICLES>
 		void AddParticles(PARTICLES&& src)

@@ -39,6 +39,23 @@ class MpsStats(C.Structure):
                 ("matrix_sweeps", C.c_uint64), ("mg_levels", C.c_uint64), ("mg_cells", C.c_uint64)]
 
 
+_OBS_FIELDS = ("edge_x", "top_z", "r_max_surface", "r_min_surface", "center_r2", "center_id", "center_p", "inner", "sum_d", "sum_p", "sum_dd",
+               "sum_dp", "max_dev", "h1", "h2", "p2_sum", "p2_count", "fluid", "wall", "dummy", "disabled", "p_max", "u_max2", "surface_count")
+
+
+class MpsObserveParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("surface_n", "rho_g", "surface_z", "x_h1", "x_h2", "min_n", "z_p2", "d")]
+
+
+class MpsObservables(C.Structure):
+    _fields_ = [(k, C.c_double) for k in _OBS_FIELDS]
+
+
+class MpsWallMotion(C.Structure):
+    _fields_ = [("amplitude", C.c_double * 3), ("velocity", C.c_double * 3), ("omega", C.c_double), ("phase", C.c_double),
+                ("t_begin", C.c_double), ("t_end", C.c_double)]
+
+
 class MpsError(RuntimeError):
     """Carries the mps_status; codes 1 / 2 correspond to Computer::Exception / Grid::Exception of the reference."""
 
@@ -77,6 +94,7 @@ def load_library():
     sig("mps_download", [vp, vp, vp, vp, vp, vp])
     sig("mps_upload", [vp, vp, vp, vp, vp])
     sig("mps_set_wall_positions", [vp, u64, vp, vp])
+    sig("mps_set_wall_motion", [vp, u64, vp, C.POINTER(MpsWallMotion)])
     sig("mps_determine_dt", [vp, pd])
     sig("mps_forward_time", [vp, dbl])
     sig("mps_forward_time_auto", [vp])
@@ -96,6 +114,7 @@ def load_library():
     sig("mps_get_vec", [vp, C.c_int, vp])
     sig("mps_set_system", [vp, u64, vp, vp, vp, vp, vp])
     sig("mps_get_solution", [vp, u64, vp])
+    sig("mps_observe", [vp, C.POINTER(MpsObserveParams), C.POINTER(MpsObservables)])
     sig("mps_set_stage_timing", [vp, C.c_int])
     sig("mps_get_stats", [vp, C.POINTER(MpsStats)])
     sig("mps_reset_stats", [vp])
@@ -211,6 +230,19 @@ class GpuComputer:
         ids = np.ascontiguousarray(ids, np.uint64); x = _f64(x)
         self._check(self.lib.mps_set_wall_positions(self.h, len(ids), _ptr(ids), _ptr(x)))
 
+    def set_wall_motion(self, ids=None, amplitude=(0, 0, 0), velocity=(0, 0, 0), omega=0.0, phase=0.0, t_begin=0.0, t_end=float("inf"), clear=False):
+        """mps_set_wall_motion: the listed (default: all non-fluid) particles follow an analytic motion evaluated on the device."""
+        if clear:
+            self._check(self.lib.mps_set_wall_motion(self.h, 0, None, None))
+            return
+        pad = lambda v: tuple(float(c) for c in v) + (0.0,) * (3 - len(v))  # noqa: E731
+        m = MpsWallMotion((C.c_double * 3)(*pad(amplitude)), (C.c_double * 3)(*pad(velocity)), omega, phase, t_begin, t_end)
+        if ids is None:
+            self._check(self.lib.mps_set_wall_motion(self.h, 0, None, C.byref(m)))
+        else:
+            ids = np.ascontiguousarray(ids, np.uint64)
+            self._check(self.lib.mps_set_wall_motion(self.h, len(ids), _ptr(ids), C.byref(m)))
+
     # ---- environment / time ----
     def env_info(self):
         info = MpsEnvInfo()
@@ -324,6 +356,13 @@ class GpuComputer:
         return out
 
     # ---- measurement ----
+    def observe(self, surface_n=0.0, rho_g=0.0, surface_z=0.0, x_h1=0.0, x_h2=0.0, min_n=float("inf"), z_p2=0.0, d=0.0):
+        """mps_observe: the benchmark observables of the resident state, reduced on the device (see observables.device_*)."""
+        prm = MpsObserveParams(surface_n, rho_g, surface_z, x_h1, x_h2, min_n, z_p2, d)
+        out = MpsObservables()
+        self._check(self.lib.mps_observe(self.h, C.byref(prm), C.byref(out)))
+        return {k: getattr(out, k) for k in _OBS_FIELDS}
+
     def set_stage_timing(self, on):
         self._check(self.lib.mps_set_stage_timing(self.h, int(on)))
 

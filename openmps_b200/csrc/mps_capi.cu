@@ -105,6 +105,7 @@ int ensure_particle_capacity(mps_solver* s, uint64_t n_exact)
 	}
 	CU(s->inv.ensure(n, st, old));
 	CU(s->wall.ensure(n * vs, st, old * vs));
+	CU(s->wall_group.ensure(n, st, old));
 	CU(s->nws.ensure(n, st, old)); CU(s->ecs.ensure(n, st, old));
 	CU(s->du.ensure(n * vs, st, old * vs)); CU(s->x0.ensure(n * vs, st, old * vs));
 	return MPS_OK;
@@ -403,6 +404,39 @@ int mps_set_wall_positions(mps_handle s, uint64_t n, const uint64_t* ids, const 
 	CU(cudaMemcpyAsync(dx, x, n * D * sizeof(double), cudaMemcpyHostToDevice, s->stream));
 	CU(cudaMemcpyAsync(dids, ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
 	CU(launch_set_wall(s, n, dids, dx));
+	CU(cudaStreamSynchronize(s->stream));
+	return MPS_OK;
+}
+
+int mps_set_wall_motion(mps_handle s, uint64_t n, const uint64_t* ids, const mps_wall_motion* motion)
+{
+	NEED(s);
+	cudaSetDevice(s->device);
+	if (!motion)
+	{
+		// back to positionWall = wall[] for everybody
+		if (s->n) CU(cudaMemsetAsync(s->wall_group.p, 0, s->n, s->stream));
+		s->motions = WallMotions{};
+		return MPS_OK;
+	}
+	if (s->motions.count >= kMaxWallMotions) return fail(s, MPS_BAD_ARG, "too many wall motions on this handle (8)");
+	if (!(motion->t_end >= motion->t_begin)) return fail(s, MPS_BAD_ARG, "wall motion: t_end < t_begin");
+	const uint64_t count = ids ? n : s->n;
+	if (count == 0) return MPS_OK;
+	const uint64_t* dids = nullptr;
+	if (ids)
+	{
+		for (uint64_t k = 0; k < n; k++) if (ids[k] >= s->n) return fail(s, MPS_BAD_ARG, "particle id out of range");
+		CU(s->stage_d.ensure(n, s->stream));
+		CU(cudaMemcpyAsync(s->stage_d.p, ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+		dids = reinterpret_cast<const uint64_t*>(s->stage_d.p);
+	}
+	WallMotion& m = s->motions.m[s->motions.count];
+	for (int a = 0; a < 3; a++) { m.amp[a] = motion->amplitude[a]; m.vel[a] = motion->velocity[a]; }
+	if (s->env.dim == 2) { m.amp[2] = 0; m.vel[2] = 0; }
+	m.omega = motion->omega; m.phase = motion->phase; m.t0 = motion->t_begin; m.t1 = motion->t_end;
+	s->motions.count += 1;
+	CU(launch_set_wall_group(s, count, dids, s->motions.count));
 	CU(cudaStreamSynchronize(s->stream));
 	return MPS_OK;
 }
@@ -792,6 +826,16 @@ int mps_debug_mg(mps_handle s, int level, int which, void* out, uint64_t capacit
 }
 
 // ---- measurement -----------------------------------------------------------------------------------------------------
+int mps_observe(mps_handle s, const mps_observe_params* params, mps_observables* out)
+{
+	NEED(s);
+	if (!params || !out) return fail(s, MPS_BAD_ARG, "mps_observe: null argument");
+	static_assert(sizeof(mps_observables) == 24 * sizeof(double), "mps_observables is the kernel's slot array");
+	CU(cudaSetDevice(s->device));
+	CU(launch_observe(s, params, reinterpret_cast<double*>(out)));
+	return MPS_OK;
+}
+
 int mps_set_stage_timing(mps_handle s, int on) { NEED(s); s->stage_timing = on != 0; return MPS_OK; }
 int mps_get_stats(mps_handle s, mps_stats* out)
 {

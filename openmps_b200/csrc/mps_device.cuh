@@ -45,6 +45,14 @@ struct EnvConst
 	double ds_d2;      // (L_0 - MaxDx)^2                  (Computer.hpp:1572,1586)
 };
 
+// Analytic wall motions evaluated on the device (mps_set_wall_motion; the reference evaluates a host callback positionWall(i, t, dt)
+// per non-fluid particle and step, Computer.hpp:993,1012-1019).  A particle of group g follows
+//   x(t) = base + vel * tau + amp * (sin(omega * tau + phase) - sin(phase)),   tau = clamp(t - t0, 0, t1 - t0)
+// with base = its wall[] entry (the position it was added with / last given by mps_set_wall_positions).
+constexpr int kMaxWallMotions = 8;
+struct WallMotion { double amp[3]; double vel[3]; double omega, phase, t0, t1; };
+struct WallMotions { int count; int pad_; WallMotion m[kMaxWallMotions]; };
+
 // Scalars that live on the device so that a step needs no host round trip.
 struct DevScalars
 {

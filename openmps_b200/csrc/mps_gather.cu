@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_explicit_accel(uint64_t first, uin
 // Computer::ComputeExplicitForces, second loop, Computer.hpp:996-1020
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_explicit_move(uint64_t first, uint64_t n, Particles<D> P, const Vec<D>* __restrict__ a,
-	const Vec<D>* __restrict__ wall /* original order */, const DevScalars* __restrict__ sc)
+	const Vec<D>* __restrict__ wall /* original order */, const uint8_t* __restrict__ wall_group, const WallMotions wm, const DevScalars* __restrict__ sc)
 {
 	const uint64_t i = first + static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (i >= n) return;
@@ -261,7 +261,18 @@ __global__ void __launch_bounds__(kThreads) k_explicit_move(uint64_t first, uint
 	else
 	{
 		// Wall, Dummy and Disabled particles follow positionWall (Computer.hpp:1011-1019)
-		const Vec<D> xw = wall[P.orig[i]];
+		const uint32_t o = P.orig[i];
+		Vec<D> xw = wall[o];
+		const int grp = wm.count ? wall_group[o] : 0;
+		if (grp)
+		{
+			// positionWall(i, t, dt) for an analytic motion, t = Environment::T() after SetNextT (Computer.hpp:921,1703-1706)
+			const WallMotion& m = wm.m[grp - 1];
+			const double tau = fmin(fmax(sc->t - m.t0, 0.0), m.t1 - m.t0);
+			const double sw = sin(m.omega * tau + m.phase) - sin(m.phase);
+#pragma unroll
+			for (int k = 0; k < D; k++) xw.v[k] = xw.v[k] + (m.vel[k] * tau + m.amp[k] * sw);
+		}
 #pragma unroll
 		for (int k = 0; k < D; k++) { u.v[k] = (xw.v[k] - x.v[k]) / dt; x.v[k] = xw.v[k]; }
 	}
@@ -575,14 +586,14 @@ __global__ void k_set_dt(DevScalars* sc, double dt_in, int advance, int from_max
 // ---- original order <-> slot order --------------------------------------------------------------------------------
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_scatter_from_orig(uint64_t first, uint64_t count, bool append, Particles<D> P,
-	uint32_t* __restrict__ inv, Vec<D>* __restrict__ wall, const double* __restrict__ x, const double* __restrict__ u,
+	uint32_t* __restrict__ inv, Vec<D>* __restrict__ wall, uint8_t* __restrict__ wall_group, const double* __restrict__ x, const double* __restrict__ u,
 	const double* __restrict__ p, const double* __restrict__ nd, const int32_t* __restrict__ type)
 {
 	const uint64_t k = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
 	if (k >= count) return;
 	const uint64_t o = first + k;
 	uint64_t s;
-	if (append) { s = o; inv[o] = static_cast<uint32_t>(o); P.orig[s] = static_cast<uint32_t>(o); }
+	if (append) { s = o; inv[o] = static_cast<uint32_t>(o); P.orig[s] = static_cast<uint32_t>(o); wall_group[o] = 0; }
 	else s = inv[o];
 	if (x)
 	{
@@ -627,6 +638,19 @@ __global__ void __launch_bounds__(kThreads) k_set_wall(uint64_t count, const uin
 	Vec<D> v = vzero<D>();
 	for (int a = 0; a < D; a++) v.v[a] = x[k * D + a];
 	wall[o] = v;
+}
+
+// mps_set_wall_motion: the listed particles (ids == nullptr: every non-fluid particle) join motion group `group`
+template<int D>
+__global__ void __launch_bounds__(kThreads) k_set_wall_group(uint64_t count, const uint64_t* __restrict__ ids, int group, Particles<D> P,
+	const uint32_t* __restrict__ inv, uint8_t* __restrict__ wall_group, uint64_t n)
+{
+	const uint64_t k = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	if (k >= count) return;
+	const uint64_t o = ids ? ids[k] : k;
+	if (o >= n) return;
+	if (!ids && P.type[inv[o]] == kFluid) return;
+	wall_group[o] = static_cast<uint8_t>(group);
 }
 
 // scalar (width 1) or vector (width D, padded source) per-slot array -> original order
@@ -699,7 +723,7 @@ template<int D> cudaError_t explicit_forces(mps_solver* s)
 	if (nb)
 	{
 		k_explicit_accel<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), lists(s), s->nws.p, reinterpret_cast<Vec<D>*>(s->du.p), s->env);
-		k_explicit_move<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), reinterpret_cast<Vec<D>*>(s->wall.p), s->d_sc);
+		k_explicit_move<D><<<nb, kThreads, 0, s->stream>>>(r0, r1, view<D>(s), reinterpret_cast<Vec<D>*>(s->du.p), reinterpret_cast<Vec<D>*>(s->wall.p), s->wall_group.p, s->motions, s->d_sc);
 		s->stats.kernel_launches += 2;
 	}
 	MPS_TRY(comm_allgather_state(s, true, true, false)); // everybody needs the moved x, u
@@ -837,7 +861,7 @@ template<int D> cudaError_t scatter_from_orig(mps_solver* s, const double* x, co
 {
 	if (count == 0) return cudaSuccess;
 	k_scatter_from_orig<D><<<blocks_for(count, kThreads), kThreads, 0, s->stream>>>(first, count, append, view<D>(s), s->inv.p,
-		reinterpret_cast<Vec<D>*>(s->wall.p), x, u, p, nd, type);
+		reinterpret_cast<Vec<D>*>(s->wall.p), s->wall_group.p, x, u, p, nd, type);
 	s->stats.kernel_launches += 1;
 	return cudaGetLastError();
 }
@@ -852,6 +876,13 @@ template<int D> cudaError_t set_wall(mps_solver* s, uint64_t count, const uint64
 {
 	if (count == 0) return cudaSuccess;
 	k_set_wall<D><<<blocks_for(count, kThreads), kThreads, 0, s->stream>>>(count, ids, x, reinterpret_cast<Vec<D>*>(s->wall.p), s->n);
+	s->stats.kernel_launches += 1;
+	return cudaGetLastError();
+}
+template<int D> cudaError_t set_wall_group(mps_solver* s, uint64_t count, const uint64_t* ids, int group)
+{
+	if (count == 0) return cudaSuccess;
+	k_set_wall_group<D><<<blocks_for(count, kThreads), kThreads, 0, s->stream>>>(count, ids, group, view<D>(s), s->inv.p, s->wall_group.p, s->n);
 	s->stats.kernel_launches += 1;
 	return cudaGetLastError();
 }
@@ -917,6 +948,7 @@ cudaError_t launch_gather_to_orig(mps_solver* s, double* d_x, double* d_u, doubl
 {
 	return MPS_DISPATCH(gather_to_orig, s, d_x, d_u, d_p, d_n, d_type);
 }
+cudaError_t launch_set_wall_group(mps_solver* s, uint64_t count, const uint64_t* d_ids, int group) { return MPS_DISPATCH(set_wall_group, s, count, d_ids, group); }
 cudaError_t launch_set_wall(mps_solver* s, uint64_t count, const uint64_t* d_ids, const double* d_x) { return MPS_DISPATCH(set_wall, s, count, d_ids, d_x); }
 cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out) { return MPS_DISPATCH(vec_to_orig, s, which, d_out); }
 

@@ -15,6 +15,7 @@
 //   scan          C x 12 B
 //   k_scatter     N x 16 B ; k_rank_fix N x (4 + occupancy x 4) ; k_reorder N x 2 x (16D + 16 + 1 + 4 + 4)
 //   k_search<false/true>  N x (pos of ~3^D cells from L1/L2) -> counts / list
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -194,16 +195,27 @@ __global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n,
 	if (!FILL) nbr_cnt[i] = cnt;
 }
 
-// Multi-GPU: slab boundaries of this step.  The nominal split is equal counts of the slots that lie in the grid; every boundary
-// then moves up to the next boundary between cell COLUMNS (all cells of one x index) whose index is a multiple of 2^a, so that
-// cells — and the 2^a-column blocks of the preconditioner's first a levels — are never shared between ranks.  a is the largest
-// value <= a_max for which every rank still gets at least one block of columns; out = [R + 1 slots | R + 1 columns | a | ok].
+// Multi-GPU: slab boundaries of this step.  The nominal split is equal shares of the modelled WORK of the slots that lie in the
+// grid (a Fluid particle carries a full PPE row and every gather stage, a Wall particle a short row, a Dummy particle only shows
+// up in other particles' lists: weights w_type, prefix sums over the sorted slots in `wprefix`); every boundary then moves up to
+// the next boundary between cell COLUMNS (all cells of one x index) whose index is a multiple of 2^a, so that cells — and the
+// 2^a-column blocks of the preconditioner's first a levels — are never shared between ranks.  a is the largest value <= a_max for
+// which every rank still gets at least one block of columns; out = [R + 1 slots | R + 1 columns | a | ok].
 // The Disabled tail (slots behind the grid) goes to the last rank.  One thread: R binary searches over the cell table.
+__global__ void __launch_bounds__(kThreads) k_slot_weight(const uint64_t n, const uint8_t* __restrict__ type, const uint32_t w_fluid, const uint32_t w_wall,
+	const uint32_t w_dummy, uint32_t* __restrict__ w)
+{
+	const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+	if (i >= n) return;
+	const uint8_t t = type[i];
+	w[i] = (t == kFluid) ? w_fluid : (t == kWall) ? w_wall : (t == kDummy) ? w_dummy : 0u;
+}
 __global__ void k_slab_bounds(const int R, const uint64_t n, const uint64_t ncells, const uint32_t ncols, const uint64_t colstride, const int a_max,
-	const uint64_t* __restrict__ cell_start, unsigned long long* __restrict__ out)
+	const uint64_t* __restrict__ cell_start, const uint64_t* __restrict__ wprefix, unsigned long long* __restrict__ out)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	const uint64_t in_grid = cell_start[ncells];
+	const uint64_t total = wprefix[in_grid];
 	int a = a_max;
 	bool ok = false;
 	for (; a >= 0 && !ok; a--)
@@ -218,13 +230,20 @@ __global__ void k_slab_bounds(const int R, const uint64_t n, const uint64_t ncel
 			else if (r == R) { col = units * unit; slot = n; }
 			else
 			{
-				const uint64_t target = in_grid / R * r + in_grid % R * r / R;
-				uint32_t lo = 0, hi = units; // smallest block of columns whose first slot is >= target
+				const uint64_t target = total / R * r + total % R * r / R;
+				uint32_t lo = 0, hi = units; // smallest block of columns whose first slot has at least `target` work before it
 				while (lo < hi)
 				{
 					const uint32_t mid = (lo + hi) >> 1;
 					const uint64_t c = static_cast<uint64_t>(mid) * unit;
-					if (cell_start[(c < ncols ? c : ncols) * colstride] < target) lo = mid + 1; else hi = mid;
+					if (wprefix[cell_start[(c < ncols ? c : ncols) * colstride]] < target) lo = mid + 1; else hi = mid;
+				}
+				// nearest boundary, not the next one: the block below may be closer to the target
+				if (lo > 0 && lo > prev / unit + 1)
+				{
+					const uint64_t cb = static_cast<uint64_t>(lo - 1) * unit, ca = static_cast<uint64_t>(lo) * unit;
+					const uint64_t wb = wprefix[cell_start[(cb < ncols ? cb : ncols) * colstride]], wa = wprefix[cell_start[(ca < ncols ? ca : ncols) * colstride]];
+					if (target - wb < wa - target) lo -= 1;
 				}
 				col = lo * unit;
 				slot = cell_start[(col < ncols ? col : ncols) * colstride];
@@ -298,16 +317,35 @@ cudaError_t sort_and_search(mps_solver* s)
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(s->cell_count.p, s->cell_start.p, env.ncells + 1, s->scan_tmp, st, &s->stats.kernel_launches));
 	// 2b. occupied cells -> compact ids: level 0 of the multigrid preconditioner's cell hierarchy (mps_mg.cu)
 	MPS_TRY(launch_mg_rank0(s));
-	// 2c. multi-GPU: this step's slab boundaries, on cell columns (one extra, tiny host round trip per step)
+	// 3. scatter, deterministic order inside each cell, permute the state
+	k_scatter<<<nb, kThreads, 0, st>>>(n, s->key.p, s->rank.p, s->cell_start.p, cur.orig, s->perm.p, s->perm_orig.p);
+	k_rank_fix<<<nb, kThreads, 0, st>>>(n, static_cast<uint32_t>(env.ncells), s->key.p, s->cell_start.p, s->perm.p, s->perm_orig.p, s->perm2.p);
+	k_reorder<D><<<nb, kThreads, 0, st>>>(n, s->perm2.p, s->key.p, cur, next, s->skey.p, s->inv.p);
+	s->cur = nxt;
+	s->stats.kernel_launches += 4;
+
+	// 3b. multi-GPU: this step's slab boundaries, on cell columns, equal shares of the modelled work (one extra, tiny host round trip per step)
 	if (s->comm.on)
 	{
 		const int R = s->comm.nranks;
 		MPS_TRY(s->d_bounds.ensure(2ull * R + 4, st));
 		const uint64_t colstride = env.ncells / static_cast<uint64_t>(env.grid_n[0]);
-		int a_max = s->mg.on ? kMgMaxDistLevels : 0;
+		// alignment 2^a columns, a = the number of leading levels of the cell hierarchy that are worth distributing (as mg_ensure
+		// will decide from this step's count; here from the previous step's, or the dense grid on the first step)
+		int a_max = 0;
+		if (s->mg.on)
+		{
+			uint64_t est = s->mg.cells0 ? s->mg.cells0 : env.ncells;
+			while (a_max < kMgMaxDistLevels && est > s->mg.dist_cells) { a_max++; est >>= env.dim; }
+		}
 		if (const char* v = std::getenv("MPS_SLAB_ALIGN")) { const int k = std::atoi(v); if (k >= 0 && k <= kMgMaxDistLevels) a_max = k; }
-		k_slab_bounds<<<1, 32, 0, st>>>(R, n, env.ncells, static_cast<uint32_t>(env.grid_n[0]), colstride, a_max, s->cell_start.p, s->d_bounds.p);
-		s->stats.kernel_launches += 1;
+		// work per sorted slot by particle type (scratch: rank[] is free after the scatter, nbr_ptr[] is rebuilt by the search below)
+		uint32_t w[3] = { 8, 4, 1 };
+		if (const char* v = std::getenv("MPS_SLAB_WEIGHTS")) { unsigned a = 0, b = 0, c = 0; if (std::sscanf(v, "%u,%u,%u", &a, &b, &c) == 3 && a + b + c > 0) { w[0] = a; w[1] = b; w[2] = c; } }
+		k_slot_weight<<<nb, kThreads, 0, st>>>(n, next.type, w[0], w[1], w[2], s->rank.p);
+		MPS_TRY(launch_exclusive_scan_u32_to_u64(s->rank.p, s->nbr_ptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
+		k_slab_bounds<<<1, 32, 0, st>>>(R, n, env.ncells, static_cast<uint32_t>(env.grid_n[0]), colstride, a_max, s->cell_start.p, s->nbr_ptr.p, s->d_bounds.p);
+		s->stats.kernel_launches += 2;
 		std::vector<unsigned long long> hb(2ull * R + 4);
 		MPS_TRY(cudaMemcpyAsync(hb.data(), s->d_bounds.p, hb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		MPS_TRY(cudaStreamSynchronize(st));
@@ -318,13 +356,6 @@ cudaError_t sort_and_search(mps_solver* s)
 		s->slab_align = static_cast<int>(hb[2 * R + 2]);
 		s->own_n = n;
 	}
-	// 3. scatter, deterministic order inside each cell, permute the state
-	k_scatter<<<nb, kThreads, 0, st>>>(n, s->key.p, s->rank.p, s->cell_start.p, cur.orig, s->perm.p, s->perm_orig.p);
-	k_rank_fix<<<nb, kThreads, 0, st>>>(n, static_cast<uint32_t>(env.ncells), s->key.p, s->cell_start.p, s->perm.p, s->perm_orig.p, s->perm2.p);
-	k_reorder<D><<<nb, kThreads, 0, st>>>(n, s->perm2.p, s->key.p, cur, next, s->skey.p, s->inv.p);
-	s->cur = nxt;
-	s->stats.kernel_launches += 4;
-
 	// 4. neighbour list: count -> row pointers -> fill
 	// lists are built for the rows this rank owns (all of them on one GPU)
 	const Vec<D>* pos = next.pos;

@@ -169,6 +169,8 @@ struct mps_solver
 	mps::DevBuf<uint32_t> orig[2];
 	mps::DevBuf<uint32_t> inv;             // original id -> slot
 	mps::DevBuf<double> wall;              // target position of non-fluid particles, ORIGINAL order, vec_stride doubles
+	mps::DevBuf<uint8_t> wall_group;       // ORIGINAL order: 0 = follows wall[], g = wall[] + motions.m[g - 1](t) (mps_set_wall_motion)
+	mps::WallMotions motions{};            // analytic wall motions evaluated inside k_explicit_move
 
 	// scratch per particle
 	mps::DevBuf<double> nws, ecs, du, x0;  // du, x0: vec_stride doubles
@@ -199,6 +201,8 @@ struct mps_solver
 
 	mps::DevScalars* d_sc = nullptr;       // device
 	mps::DevScalars* h_sc = nullptr;       // pinned host mirror
+
+	mps::DevBuf<double> obs;               // observables: [result | per-block partials] (mps_observe.cu)
 
 	// L2 flush buffer
 	mps::DevBuf<char> flush;
@@ -252,6 +256,7 @@ cudaError_t launch_dndt_one(mps_solver* s, uint64_t orig_id, double* d_out);
 cudaError_t launch_scatter_from_orig(mps_solver* s, const double* d_x, const double* d_u, const double* d_p, const double* d_n,
 	const int32_t* d_type, uint64_t first, uint64_t count, bool append);
 cudaError_t launch_gather_to_orig(mps_solver* s, double* d_x, double* d_u, double* d_p, double* d_n, int32_t* d_type);
+cudaError_t launch_set_wall_group(mps_solver* s, uint64_t count, const uint64_t* d_ids, int group); // d_ids == nullptr: every non-fluid particle
 cudaError_t launch_set_wall(mps_solver* s, uint64_t count, const uint64_t* d_ids, const double* d_x);
 cudaError_t launch_gather_vec_to_orig(mps_solver* s, int which, double* d_out);
 // mps_comm.cu
@@ -262,6 +267,8 @@ cudaError_t comm_allreduce_sum(mps_solver* s, double* p, uint64_t count);       
 double* comm_mg_section(mps_solver* s, int rank);                               // the mg section of `rank`'s arena as mapped here
 cudaError_t comm_prepare_link(mps_solver* s);                                   // halo extents -> comm.link for the next persistent solve
 void comm_release_peers(mps_solver* s);
+// mps_observe.cu
+cudaError_t launch_observe(mps_solver* s, const mps_observe_params* p, double* host_out); // 24 doubles, synchronises
 // mps_scan.cu
 cudaError_t launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /* n + 1 */, uint64_t n, DevBuf<uint64_t>& tmp, cudaStream_t st,
 	uint64_t* launches);

@@ -77,3 +77,34 @@ def hydrostatic(state, rho, g, surface_z=None):
     slope = float(np.polyfit(depth[inner], p[inner], 1)[0])
     dev = float(np.abs(p[inner] - rho * g * depth[inner]).max() / (rho * g * h))
     return {"slope_by_rho_g": slope / (rho * g), "max_rel_dev": dev, "h": h}
+
+
+# ---- the same observables from the device reductions of mps_observe (csrc/mps_observe.cu): no state download ----------------
+def device_dam_break_edge(gpu):
+    """dam_break_edge() of the state resident on the GPU (one reduction pass, 24 doubles back)."""
+    return gpu.observe()["edge_x"]
+
+
+def device_probes(gpu, min_n, x_h1=2020e-3 - 1525e-3, x_h2=2020e-3 - 1028e-3, z_p2=160e-3, d=90e-3):
+    o = gpu.observe(x_h1=x_h1, x_h2=x_h2, min_n=min_n, z_p2=z_p2, d=d)
+    return {"h1": o["h1"], "h2": o["h2"], "p2": o["p2_sum"] / o["p2_count"] if o["p2_count"] else float("nan")}
+
+
+def device_central_gravity(gpu, r_e_by_l0, beta, L):
+    o = gpu.observe(surface_n=lattice_n0_2d(r_e_by_l0) * beta)
+    R = L / math.sqrt(math.pi)
+    roundness = float("nan") if o["surface_count"] == 0 else 1.0 - (o["r_max_surface"] - o["r_min_surface"]) / R
+    return {"roundness_percent": 100.0 * roundness, "p_center": o["center_p"], "p_theoretical": 1000 * 9.8 * R, "R": R}
+
+
+def device_hydrostatic(gpu, rho, g, surface_z=None):
+    """hydrostatic() from the moments the device returns: slope = (N S_dp - S_d S_p) / (N S_dd - S_d^2)."""
+    h = gpu.observe()["top_z"] if surface_z is None else float(surface_z)
+    o = gpu.observe(rho_g=rho * g, surface_z=h)
+    N = o["inner"]
+    if N < 2:
+        return {"slope_by_rho_g": float("nan"), "max_rel_dev": float("nan"), "h": h}
+    # centred moments (the raw form cancels badly when the depths are close together)
+    md, mp = o["sum_d"] / N, o["sum_p"] / N
+    slope = (o["sum_dp"] - N * md * mp) / (o["sum_dd"] - N * md * md)
+    return {"slope_by_rho_g": slope / (rho * g), "max_rel_dev": o["max_dev"] / (rho * g * h), "h": h}

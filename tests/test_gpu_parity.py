@@ -313,3 +313,49 @@ def test_preconditioned_solve_same_answer_far_fewer_sweeps(make, steps, monkeypa
     assert lv_plain == 0 and lv_pcg >= 2
     assert rel_err(x_pcg, x_plain) <= CG_TOL
     assert it_pcg * 5 <= it_plain, (it_pcg, it_plain)
+
+
+def _wall_motion_positions(base, t, amp, vel, omega, phase, t0, t1):
+    tau = min(max(t - t0, 0.0), t1 - t0)
+    return base + np.asarray(vel) * tau + np.asarray(amp) * (np.sin(omega * tau + phase) - np.sin(phase))
+
+
+@pytest.mark.parametrize("make,steps,motion", [
+    # a piston: the left wall of the sample tank (Wall + Dummy columns with x < 0) pushed into the water at 5 cm/s with a shake on top
+    (lambda: scenes.dambreak2d(), 60, dict(amplitude=(4e-4, 0.0), velocity=(0.05, 0.0), omega=300.0, phase=0.3, t_begin=2e-3, t_end=2.4e-2)),
+    # a sloshing tank in 3-D: every non-fluid particle shaken along x
+    (lambda: scenes.dambreak3d(l0=0.035), 8, dict(amplitude=(2e-3, 0.0, 5e-4), velocity=(0.0, 0.0, 0.0), omega=400.0, phase=0.0, t_begin=0.0, t_end=1.0)),
+])
+def test_device_evaluated_wall_motion_matches_host_callback(make, steps, motion):
+    """SURVEY 8f rank 4 (Computer.hpp:993,1012-1019): positionWall(i, t, dt) of an analytic motion evaluated inside k_explicit_move
+    (mps_set_wall_motion) == the CPU restatement fed, step by step, with the same motion evaluated on the host the way the reference
+    calls its callback (t = Environment::T() after SetNextT)."""
+    sc = make()
+    p, g = _port_and_gpu(sc)
+    D = sc.env.dim
+    nonfluid = np.flatnonzero(sc.type != 0)
+    ids = nonfluid[sc.x[nonfluid, 0] < 0] if D == 2 else nonfluid
+    assert len(ids) > 10
+    g.set_wall_motion(ids=(ids if D == 2 else None), **motion)
+    base = sc.x[ids].copy()
+    kw = dict(amp=motion["amplitude"], vel=motion["velocity"], omega=motion["omega"], phase=motion["phase"], t0=motion["t_begin"], t1=motion["t_end"])
+    for _ in range(steps):
+        dt = p.determine_dt()
+        t_next = p.env_values()["t"] + dt
+        p.set_wall_positions(ids, _wall_motion_positions(base, t_next, **kw))
+        p.forward(1, dt=dt)
+        g.forward(1)
+    sp, sg = p.state(), g.state()
+    assert np.array_equal(sp["type"], sg["type"])
+    moved = np.abs(sg["x"][ids] - base).max()
+    assert moved > 1e-4                                   # the wall really moved ...
+    assert rel_err(sg["x"][ids], sp["x"][ids]) <= 1e-12   # ... to where the host callback puts it (device sin vs libm: an ulp or two)
+    assert rel_err(sg["u"][ids], sp["u"][ids]) <= 1e-7    # u = (x - x_prev) / dt of a sub-millimetre move: cancellation, still tiny
+    assert rel_err(sg["x"], sp["x"]) <= 1e-8
+    assert rel_err(sg["n"], sp["n"]) <= 1e-7
+    assert abs(p.env_values()["t"] - g.time()[0]) <= 1e-9 * g.time()[0]
+    # clearing the motions freezes the wall where positionWall = wall[] puts it: back at the base positions after one more step
+    g.set_wall_motion(clear=True)
+    g.forward(1)
+    assert rel_err(g.state()["x"][ids], base) <= 1e-15
+    p.close(); g.close()

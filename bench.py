@@ -82,6 +82,7 @@ WORKLOADS = {
     "dambreak3d_123k": (lambda: scenes.dambreak3d(8e-3), "DamBreak 3D l0=8e-3, 123147 particles"),
     "dambreak3d_1m": (lambda: scenes.dambreak3d(3.6e-3), "DamBreak 3D l0=3.6e-3"),
     "dambreak3d_10m": (lambda: scenes.dambreak3d(1.36e-3), "DamBreak 3D l0=1.36e-3, ~12.2M particles (~10M fluid)"),
+    "dambreak3d_100m": (lambda: scenes.dambreak3d(6.5e-4), "DamBreak 3D l0=6.5e-4, ~101M particles (~91M fluid): BASELINE.json configs[4]"),
 }
 LARGE_WORKLOAD = "dambreak3d_10m"     # BASELINE.json configs[3]: the `large` sub-record of every line (strong scaling over --gpus)
 LARGE_STEPS, LARGE_WARMUP = 3, 3

@@ -126,7 +126,18 @@ int set_dt_device(mps_solver* s, double dt, int advance, bool from_max_u)
 }
 
 // One reference time step after dt has been set and t advanced: Computer.hpp:1708-1741
+int step_stages(mps_solver* s);
 int step_body(mps_solver* s)
+{
+	// several ranks: the stages exchange halos only; one full gather of the state ends the step (mps_comm.cu comm_allgather_state)
+	s->comm.halo_step = s->comm.on;
+	const int rc = step_stages(s);
+	const bool gather_all = s->comm.halo_step && rc == MPS_OK && s->sort_error != MPS_CELL_OVERFLOW;
+	s->comm.halo_step = false;
+	if (gather_all) { StageTimer t(s, kStDs); CU(comm_allgather_state(s, true, true, true, true)); }
+	return rc;
+}
+int step_stages(mps_solver* s)
 {
 	{ StageTimer t(s, kStSearch); CU(launch_sort_and_search(s)); }
 	if (s->sort_error == MPS_CELL_OVERFLOW)
@@ -349,6 +360,8 @@ int mps_add_particles(mps_handle s, uint64_t n, const double* x, const double* u
 	CU(launch_scatter_from_orig(s, dx, du, dp, dn, s->stage_i.p, first, n, true));
 	CU(cudaStreamSynchronize(s->stream)); // the caller's buffers may be reused after return
 	s->searched = false;
+	// a staging area of gigabytes is given back (it returns with the next upload / download): at 100M particles it is 6 GB of HBM
+	if (s->stage_d.cap * sizeof(double) > (1ull << 30)) { s->stage_d.release(); s->stage_i.release(); }
 	return MPS_OK;
 }
 

@@ -338,7 +338,17 @@ cudaError_t build(mps_solver* s)
 	// capacities that need no host round trip: entries <= neighbour entries + n; every chunk pads < 16 + 16 + 16 bytes
 	const uint64_t desc_cap = n / 16 + nblk + 1024;
 	MPS_TRY(cg.desc.ensure(desc_cap, st)); MPS_TRY(cg.live.ensure(desc_cap, st));
-	const uint64_t blob_cap = (s->nbr_total + n) * 10 + n * 2 + desc_cap * (96 + kBlobHeader) + 256;
+	uint64_t entries = s->nbr_total + (s->own1() - s->own0()); // bound: the list also holds the candidates between r_e and the cell size
+	if (alloc_slack_percent() == 0)
+	{
+		// blocks that only just fit the GPU (MPS_ALLOC_SLACK=0): size the blobs from the exact entry count (the row-pointer scan has
+		// just produced it) at the price of one more host read-back per step — in 3-D the bound is 1.6x the matrix
+		uint64_t nnz = 0;
+		MPS_TRY(cudaMemcpyAsync(&nnz, cg.rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		MPS_TRY(cudaStreamSynchronize(st));
+		if (nnz < entries) entries = nnz;
+	}
+	const uint64_t blob_cap = entries * 10 + n * 2 + desc_cap * (96 + kBlobHeader) + 256;
 	MPS_TRY(cg.blobs.ensure(blob_cap, st));
 	cg.desc_cap = desc_cap;
 

@@ -78,7 +78,7 @@ struct PeerGatherArgs
 	unsigned long long* dst[4];
 	const unsigned long long* src[4][kMaxPeerRanks];
 	unsigned long long words_per_row[4];
-	unsigned long long begin[kMaxPeerRanks + 1]; // first row of every rank's slab
+	unsigned long long lo[kMaxPeerRanks], hi[kMaxPeerRanks]; // rows [lo, hi) to pull from each rank (its whole slab, or the part of it in this rank's halo)
 };
 
 #define MPS_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return e_; } while (0)
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) k_peer_gather(PeerGatherArgs a)
 		for (int r = 0; r < a.nranks; r++)
 		{
 			if (r == a.rank) continue;
-			const unsigned long long b = a.begin[r] * w, e = a.begin[r + 1] * w;
+			const unsigned long long b = a.lo[r] * w, e = a.hi[r] * w;
 			const unsigned long long* __restrict__ src = a.src[f][r];
 			for (unsigned long long i = b + tid; i < e; i += nthreads) dst[i] = src[i];
 		}
@@ -413,6 +413,10 @@ cudaError_t peer_barrier(mps_solver* s)
 // Fields that neighbours read, after the stage that wrote this rank's slab of them.  Peer memory: barrier (every rank's slab
 // is written), one kernel in which every rank copies the other slabs straight from their owners over NVLink, barrier (nobody
 // overwrites a slab a peer is still reading).  NCCL all-gathers where the ranks cannot map each other's memory.
+// Inside a time step (comm.halo_step) only the HALO is pulled: the stages of a step read other particles through the neighbour
+// list, whose candidates lie in the 3^D cell stencil, i.e. at most one cell column beyond this rank's slab on either side — one
+// contiguous range of the cell-sorted slots per adjacent rank (halo_lo / halo_hi, k_slab_bounds).  The step ends with one full
+// gather of x, u, p, n (mps_capi.cu step_body): the next sort, DetermineDt and Particles() see the whole replicated state.
 cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bool nden)
 {
 	if (!s->comm.on || s->n == 0) return cudaSuccess;
@@ -431,7 +435,19 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 			for (int r = 0; r < c.nranks; r++) a.src[q][r] = reinterpret_cast<const unsigned long long*>(c.peer_state[r][f]);
 			a.words_per_row[q] = words_per_row;
 		};
-		for (int r = 0; r <= c.nranks; r++) a.begin[r] = s->slab_begin(r);
+		const bool halo = c.halo_step && s->slabs_set() && s->halo_lo.size() == static_cast<size_t>(c.nranks);
+		for (int r = 0; r < c.nranks; r++)
+		{
+			uint64_t lo = s->slab_begin(r), hi = s->slab_begin(r + 1);
+			if (halo)
+			{
+				// my halo: [halo_lo[k], own0) in the slab of rank k - 1 and [own1, halo_hi[k]) in the slab of rank k + 1
+				if (r == k - 1) lo = std::max<uint64_t>(lo, s->halo_lo[k]);
+				else if (r == k + 1) hi = std::min<uint64_t>(hi, s->halo_hi[k]);
+				else hi = lo;
+			}
+			a.lo[r] = lo; a.hi[r] = (hi > lo) ? hi : lo;
+		}
 		if (pos) add(0, vs);
 		if (vel) add(1, vs);
 		if (prs) add(2, 1);

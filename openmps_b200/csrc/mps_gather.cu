@@ -325,10 +325,10 @@ struct PpeOut
 
 // PRE = true additionally leaves behind what the multigrid preconditioner is built from (mps_mg.cu): 1 / a_ii, and the row's
 // entries summed per cell of the 3^D stencil around the row's own cell (the cell of a slot is the one the sort put it in, so
-// every neighbour of the list lies in that stencil): row_s[s * stride + i].
+// every neighbour of the list lies in that stencil): row_s[s * stride + (i - row0)] for the rows [row0, row0 + stride) this rank owns.
 struct PpePre
 {
-	const uint32_t* skey; double* row_s; double* dinv0; uint64_t stride;
+	const uint32_t* skey; double* row_s; double* dinv0; uint64_t stride, row0;
 };
 
 template<int D, bool CHUNKED, bool PRE>
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 	{
 		pre.dinv0[i] = (a_ii != 0) ? 1.0 / a_ii : 0.0;
 #pragma unroll
-		for (int s = 0; s < K; s++) pre.row_s[static_cast<uint64_t>(s) * pre.stride + i] = sacc[s][threadIdx.x];
+		for (int s = 0; s < K; s++) pre.row_s[static_cast<uint64_t>(s) * pre.stride + (i - pre.row0)] = sacc[s][threadIdx.x];
 	}
 }
 
@@ -784,7 +784,7 @@ template<int D> cudaError_t ppe_fill(mps_solver* s, bool recount)
 		s->stats.kernel_launches += 1;
 	}
 	PpePre pre{};
-	if (pre_on) { pre.skey = s->skey.p; pre.row_s = s->mg.row_s.p; pre.dinv0 = s->mg.dinv0.p; pre.stride = n; }
+	if (pre_on) { pre.skey = s->skey.p; pre.row_s = s->mg.row_s.p; pre.dinv0 = s->mg.dinv0.p; pre.stride = r1 - r0; pre.row0 = r0; }
 	if (nb)
 	{
 		if (cg.chunked && pre_on)

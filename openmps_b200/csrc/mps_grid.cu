@@ -255,6 +255,14 @@ __global__ void k_slab_bounds(const int R, const uint64_t n, const uint64_t ncel
 		if (ok) { out[2 * R + 2] = static_cast<unsigned long long>(a); break; }
 	}
 	out[2 * R + 3] = ok ? 1ull : 0ull;
+	// halo of every slab: one cell column on either side (the neighbour stencil is 3 cells wide)
+	for (int r = 0; r < R; r++)
+	{
+		const uint64_t c0 = out[R + 1 + r], c1 = out[R + 1 + r + 1];
+		const uint64_t cl = (c0 > 0) ? c0 - 1 : 0, ch = (c1 + 1 < ncols) ? c1 + 1 : ncols;
+		out[2 * R + 4 + r] = cell_start[(cl < ncols ? cl : ncols) * colstride];
+		out[3 * R + 4 + r] = cell_start[(ch < ncols ? ch : ncols) * colstride];
+	}
 }
 
 template<int D>
@@ -328,7 +336,7 @@ cudaError_t sort_and_search(mps_solver* s)
 	if (s->comm.on)
 	{
 		const int R = s->comm.nranks;
-		MPS_TRY(s->d_bounds.ensure(2ull * R + 4, st));
+		MPS_TRY(s->d_bounds.ensure(4ull * R + 4, st));
 		const uint64_t colstride = env.ncells / static_cast<uint64_t>(env.grid_n[0]);
 		// alignment 2^a columns, a = the number of leading levels of the cell hierarchy that are worth distributing (as mg_ensure
 		// will decide from this step's count; here from the previous step's, or the dense grid on the first step)
@@ -346,7 +354,7 @@ cudaError_t sort_and_search(mps_solver* s)
 		MPS_TRY(launch_exclusive_scan_u32_to_u64(s->rank.p, s->nbr_ptr.p, n, s->scan_tmp, st, &s->stats.kernel_launches));
 		k_slab_bounds<<<1, 32, 0, st>>>(R, n, env.ncells, static_cast<uint32_t>(env.grid_n[0]), colstride, a_max, s->cell_start.p, s->nbr_ptr.p, s->d_bounds.p);
 		s->stats.kernel_launches += 2;
-		std::vector<unsigned long long> hb(2ull * R + 4);
+		std::vector<unsigned long long> hb(4ull * R + 4);
 		MPS_TRY(cudaMemcpyAsync(hb.data(), s->d_bounds.p, hb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		MPS_TRY(cudaStreamSynchronize(st));
 		if (!hb[2 * R + 3]) { s->comm_error = "fewer cell columns than GPUs: use fewer GPUs for this problem"; return cudaErrorUnknown; }
@@ -354,6 +362,8 @@ cudaError_t sort_and_search(mps_solver* s)
 		s->col_b.resize(R + 1);
 		for (int r = 0; r <= R; r++) s->col_b[r] = static_cast<uint32_t>(hb[R + 1 + r]);
 		s->slab_align = static_cast<int>(hb[2 * R + 2]);
+		s->halo_lo.assign(hb.begin() + 2 * R + 4, hb.begin() + 3 * R + 4);
+		s->halo_hi.assign(hb.begin() + 3 * R + 4, hb.begin() + 4 * R + 4);
 		s->own_n = n;
 	}
 	// 4. neighbour list: count -> row pointers -> fill

@@ -161,10 +161,11 @@ __global__ void __launch_bounds__(kThreads) k_mg_cstart(uint64_t bound, const ui
 }
 
 // level-0 operator: S[c][s] = sum over the ACTIVE rows of cell c of the per-row stencil sums written by k_ppe_fill
-// (row_s[s * stride + row]); fixed order => run-to-run identical
+// (row_s[s * stride + (row - row0)], rows [row0, row0 + stride) = this rank's); fixed order => run-to-run identical.  Cells of
+// other ranks get 0 (several ranks: their operators are summed in at the gathered level, k_mg_mask + all-reduce).
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_mg_s0(uint64_t bound, const uint64_t* __restrict__ count, const uint64_t* __restrict__ cstart,
-	const uint32_t* __restrict__ row_len, const double* __restrict__ row_s, uint64_t stride, double* __restrict__ S, double* __restrict__ dinv, double omega)
+	const uint32_t* __restrict__ row_len, const double* __restrict__ row_s, uint64_t stride, uint64_t row0, double* __restrict__ S, double* __restrict__ dinv, double omega)
 {
 	constexpr int K = (D == 3) ? 27 : 9;
 	const uint64_t t = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kThreads) k_mg_s0(uint64_t bound, const uint64
 	if (cc >= bound || cc >= *count) return;
 	double sum = 0.0;
 	for (uint64_t r = cstart[cc]; r < cstart[cc + 1]; r++)
-		if (row_len[r]) sum += row_s[static_cast<uint64_t>(s) * stride + r];
+		if (r >= row0 && r - row0 < stride && row_len[r]) sum += row_s[static_cast<uint64_t>(s) * stride + (r - row0)];
 	S[cc * K + s] = sum;
 	if (s == K / 2) dinv[cc] = (sum != 0.0) ? omega / sum : 0.0;
 }
@@ -286,7 +287,7 @@ cudaError_t setup(mps_solver* s)
 	k_mg_cstart<<<blocks_for(l0.bound + 1, kThreads), kThreads, 0, st>>>(l0.bound, l0.rank.p + l0.dense, s->env.ncells, l0.key.p, s->cell_start.p, mg.cstart.p);
 	L += 2;
 	// ---- operators ----
-	k_mg_s0<D><<<blocks_for(l0.bound * K, kThreads), kThreads, 0, st>>>(l0.bound, l0.rank.p + l0.dense, mg.cstart.p, s->row_len.p, mg.row_s.p, n, l0.S.p,
+	k_mg_s0<D><<<blocks_for(l0.bound * K, kThreads), kThreads, 0, st>>>(l0.bound, l0.rank.p + l0.dense, mg.cstart.p, s->row_len.p, mg.row_s.p, s->own1() - s->own0(), s->own0(), l0.S.p,
 		l0.dinv.p, mg.omega);
 	L += 1;
 	for (int l = 0; l < mg.levels; l++)
@@ -399,7 +400,7 @@ cudaError_t mg_ensure(mps_solver* s, uint64_t cells0)
 	}
 	MPS_TRY(mg.crow.ensure(s->n + 64, st)); MPS_TRY(mg.cstart.ensure(cells0 + 2, st));
 	MPS_TRY(mg.dinv0.ensure(s->n + 64, st));
-	MPS_TRY(mg.row_s.ensure(s->n * K, st));
+	MPS_TRY(mg.row_s.ensure((s->own1() - s->own0()) * K, st)); // per-row stencil sums of the rows this rank assembles
 	return cudaSuccess;
 }
 

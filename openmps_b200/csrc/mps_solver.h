@@ -3,6 +3,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,14 @@ enum Stage
 	kStDt, kStCount
 };
 
+// head-room of a growing device buffer in percent (MPS_ALLOC_SLACK, default 25: re-allocations become rare as particles or
+// neighbours fluctuate; 0 for blocks that only just fit the GPU, e.g. 100M particles on one B200)
+inline size_t alloc_slack_percent()
+{
+	static const size_t v = [] { const char* e = std::getenv("MPS_ALLOC_SLACK"); const long k = e ? std::atol(e) : 25; return static_cast<size_t>(k < 0 ? 0 : (k > 100 ? 100 : k)); }();
+	return v;
+}
+
 template<typename T>
 struct DevBuf
 {
@@ -29,7 +38,7 @@ struct DevBuf
 	cudaError_t ensure(size_t n, cudaStream_t s = nullptr, size_t keep_n = 0)
 	{
 		if (n <= cap) return cudaSuccess;
-		size_t want = n + n / 4 + 16;
+		size_t want = n + n / 100 * alloc_slack_percent() + 16;
 		T* q = nullptr;
 		cudaError_t e = cudaMalloc(&q, want * sizeof(T));
 		if (e != cudaSuccess) { want = n; e = cudaMalloc(&q, want * sizeof(T)); }
@@ -147,6 +156,7 @@ struct Comm
 	unsigned long long bar_seq = 0;    // stream-level barriers so far (monotonic flag value)
 	uint64_t peer_gathers = 0;
 	PeerLink link{};                   // what the next solve's kernel gets
+	bool halo_step = false;            // inside ForwardTime: per-stage gathers pull the halo only (mps_comm.cu comm_allgather_state)
 };
 } // namespace mps
 
@@ -224,9 +234,10 @@ struct mps_solver
 	mps::Comm comm;
 	std::vector<uint64_t> own_b;           // [nranks + 1] first slot of every rank's slab (valid while own_n == n)
 	std::vector<uint32_t> col_b;           // [nranks + 1] first cell column of every rank's slab
+	std::vector<uint64_t> halo_lo, halo_hi; // [nranks] slots [halo_lo[r], own_b[r]) and [own_b[r + 1], halo_hi[r]): one cell column either side of slab r
 	uint64_t own_n = ~0ull;
 	int slab_align = 0;                    // slab boundaries are multiples of 2^slab_align cell columns
-	mps::DevBuf<unsigned long long> d_bounds; // device scratch of k_slab_bounds: [own_b | col_b]
+	mps::DevBuf<unsigned long long> d_bounds; // device scratch of k_slab_bounds: [own_b | col_b | a | ok | halo_lo | halo_hi]
 	bool slabs_set() const { return comm.on && own_n == n && own_b.size() == static_cast<size_t>(comm.nranks) + 1; }
 	uint64_t nominal(int r) const { const uint64_t m = (n + comm.nranks - 1) / comm.nranks, b = static_cast<uint64_t>(r) * m; return b < n ? b : n; }
 	uint64_t slab_begin(int r) const { return slabs_set() ? own_b[r] : nominal(r); }

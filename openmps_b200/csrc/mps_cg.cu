@@ -1020,8 +1020,7 @@ __device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict
 
 constexpr uint32_t kMgSmallCells = 256;  // levels with at most this many cells are run by CTA 0 alone between block barriers
 
-// several ranks: which compact cells of level l lie left of cell column `col` (slab boundaries are multiples of 2^l columns for
-// every level this is asked for, MgDist)
+// several ranks: which compact cells of level l lie left of cell column `col` (asked for level 0 only: any column is a cell boundary there)
 __device__ __forceinline__ uint32_t level_cell_begin(const MgLevelPtrs& lv, const int l, const uint32_t col)
 {
 	uint64_t idx = static_cast<uint64_t>(col >> l) * lv.colstride;
@@ -1032,10 +1031,10 @@ __device__ __forceinline__ uint32_t level_cell_begin(const MgLevelPtrs& lv, cons
 // what the V-cycle needs to know about the other ranks (all in registers / shared memory of the CTA)
 struct DistCtx
 {
-	int k;                                 // first replicated level
-	uint32_t lo[kMgMaxDistLevels + 1];     // this rank's cells of levels 0 .. k
-	uint32_t hi[kMgMaxDistLevels + 1];
-	const uint32_t* gather;                // [nranks + 1] (shared memory) cell ranges of every rank at level k
+	int k;                                 // first replicated level (0 or 1)
+	uint32_t lo[1];                        // this rank's level-0 cells
+	uint32_t hi[1];
+	const uint32_t* gather;                // [nranks + 1] (shared memory) level-0 cell ranges of every rank
 };
 
 template<bool MG>
@@ -1059,9 +1058,14 @@ __device__ __forceinline__ LevelView<MG> level_view(const MgArgs& m, const DistC
 // Levels [0, Ls) are "wide": every thread of the grid takes cells, one grid barrier per level and direction.  Levels [Ls, L) are
 // small (a few hundred cells): there a grid barrier (~1.5 us + the L2 latency of the stage behind it) would cost far more than the
 // work, so CTA 0 runs them alone between block barriers while the other CTAs wait at the grid barrier that hands the result back.
-// Several ranks (MG): levels [0, k) are distributed — own cells only, halo cells of the adjacent ranks read from their arenas,
-// and the barrier behind such a stage is the cross-rank one (all_sum<true> of nothing); level k is gathered from all ranks; the
-// levels above run replicated exactly as on one GPU.  On entry the barrier the caller went through must have been cross-rank.
+// Several ranks (MG), k = m.dist.k:
+//   k = 1  level 0 is DISTRIBUTED: a rank smooths the cells of its own slab (any cut between cell columns) and reads the halo cells
+//          of the adjacent ranks from their arenas; the restriction to level 1 is two steps — every rank leaves the level-0
+//          residual of its cells in its arena (cross-rank barrier), then EVERY rank sums the children of every level-1 cell, own
+//          ones from L2 and the others straight from their owners over NVLink — so level 1 and everything above is replicated
+//          (computed whole, on identical data, with identical results, exactly as on one GPU) without any alignment of the slabs;
+//   k = 0  small problems: level 0 is gathered from all ranks at the start and the whole cycle is replicated.
+// On entry the barrier the caller went through must have been cross-rank.
 template<int D, bool MG>
 __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const MgArgs& m, const DistCtx& dc, const int L, const int Ls,
 	unsigned long long& bar_target, unsigned long long& seq, unsigned& part_sel, double* red, const unsigned nblocks, unsigned long long* vprof)
@@ -1101,18 +1105,27 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 	for (int l = 0; l + 1 < L; l++)
 	{
 		const bool wide = (l + 1 < Ls);
-		const bool owned = MG && (l + 1 <= dc.k); // the result level is distributed or about to be gathered: own cells only
+		const bool split = MG && dc.k == 1 && l == 0; // distributed level 0 -> replicated level 1
+		if (split)
+		{
+			const MgLevelPtrs& lo = m.lv[0];
+			const LevelView<MG> ev = level_view<MG>(m, dc, 0, 1, lo.e0);
+			// step 1: residual of this rank's level-0 cells, into e1 (free until the way up)
+			for (uint64_t c = dc.lo[0] + gt; c < dc.hi[0]; c += gs)
+				lo.e1[c] = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
+			pbar();
+		}
 		if (wide || cta0)
 		{
 			const MgLevelPtrs& lo = m.lv[l];
 			const MgLevelPtrs& hi = m.lv[l + 1];
-			const uint64_t c_b = owned ? dc.lo[l + 1] : 0, c_e = owned ? dc.hi[l + 1] : *hi.count;
+			const uint64_t c_e = *hi.count;
 			const LevelView<MG> ev = level_view<MG>(m, dc, l, 1, lo.e0);
 			// CH lanes per coarse cell, one child each (the children's stencil products are independent chains of L2 round trips:
 			// side by side instead of one after the other), summed over the lanes in a fixed order
 			const uint64_t first = (wide ? gt : threadIdx.x) / CH, step = (wide ? gs : blockDim.x) / CH; // gs, blockDim.x are multiples of 32
 			const unsigned q = threadIdx.x % CH;
-			for (uint64_t C0 = c_b; C0 < c_e; C0 += step) // warp-uniform trip count
+			for (uint64_t C0 = 0; C0 < c_e; C0 += step) // warp-uniform trip count
 			{
 				const uint64_t C = C0 + first;
 				const bool on = C < c_e;
@@ -1121,7 +1134,18 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 				if (ch != kMgNone)
 				{
 					const uint64_t c = ch;
-					res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
+					if (split)
+					{
+						// step 2: the child's residual from whoever owns it (rank boundaries of the level-0 cells in dc.gather)
+						if (c >= dc.lo[0] && c < dc.hi[0]) res = __ldcg(lo.e1 + c);
+						else
+						{
+							int o = 0;
+							while (o + 1 < m.dist.nranks && c >= dc.gather[o + 1]) o++;
+							res = ld_relaxed_sys_f64(m.dist.peer_vec[o] + lo.off_e1 + c);
+						}
+					}
+					else res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
 				}
 #pragma unroll
 				for (int o = 1; o < CH; o <<= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
@@ -1132,10 +1156,8 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 				}
 			}
 		}
-		if (owned) pbar();
-		else if (wide) gbar();
+		if (wide) gbar();
 		else if (cta0) __syncthreads();
-		if (MG && l + 1 == dc.k) gather_level(dc.k);
 		lap(l);
 	}
 	// ---- top level: more damped-Jacobi sweeps, ping-pong ----
@@ -1176,7 +1198,7 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 			const MgLevelPtrs& lv = m.lv[l];
 			const uint64_t c_b = owned ? dc.lo[l] : 0, c_e = owned ? dc.hi[l] : *lv.count;
 			const LevelView<MG> ev = level_view<MG>(m, dc, l, 1, lv.e0);
-			const LevelView<MG> hv = level_view<MG>(m, dc, l + 1, 2, ehi); // a distributed upper level is never the top: its result is e1
+			const LevelView<MG> hv = level_view<MG>(m, dc, l + 1, 2, ehi); // levels above 0 are never distributed: local
 			for (uint64_t c = c_b + (wide ? gt : threadIdx.x); c < c_e; c += wide ? gs : blockDim.x)
 			{
 				const double acc = __ldcg(lv.r + c) - stencil_dot_prolong<K, MG, MG>(lv.nbr + c * K, lv.S + c * K, ev, hv, lv.parent, gamma);
@@ -1184,8 +1206,7 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 				lv.e1[c] = fma(__ldg(lv.dinv + c), acc, ecur);
 			}
 		}
-		if (owned && l > 0) pbar();      // the level below reads this rank's result as halo
-		else if (wide) gbar();           // (level 0's result is only read by its owner's rows)
+		if (wide) gbar();                // (a distributed level 0's result is only read by its owner's rows)
 		else if (cta0) __syncthreads();
 		ehi = m.lv[l].e1;
 		lap(20 + l);
@@ -1224,18 +1245,12 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 	DistCtx dc;
 	dc.k = MG ? m.dist.k : 0;
 	dc.gather = s_gather;
-#pragma unroll
-	for (int l = 0; l <= kMgMaxDistLevels; l++) { dc.lo[l] = 0; dc.hi[l] = 0; }
+	dc.lo[0] = 0; dc.hi[0] = 0;
 	if (MG)
 	{
-#pragma unroll
-		for (int l = 0; l <= kMgMaxDistLevels; l++)
-			if (l <= dc.k)
-			{
-				dc.lo[l] = level_cell_begin(m.lv[l], l, m.dist.col_b[m.dist.rank]);
-				dc.hi[l] = level_cell_begin(m.lv[l], l, m.dist.col_b[m.dist.rank + 1]);
-			}
-		if (threadIdx.x <= static_cast<unsigned>(m.dist.nranks)) s_gather[threadIdx.x] = level_cell_begin(m.lv[dc.k], dc.k, m.dist.col_b[threadIdx.x]);
+		dc.lo[0] = level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank]);
+		dc.hi[0] = level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank + 1]);
+		if (threadIdx.x <= static_cast<unsigned>(m.dist.nranks)) s_gather[threadIdx.x] = level_cell_begin(m.lv[0], 0, m.dist.col_b[threadIdx.x]);
 		__syncthreads();
 	}
 	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA); the gathered

@@ -148,7 +148,7 @@ struct PeerLink
 // ---- multigrid preconditioner on the cell hierarchy (mps_mg.cu builds it, mps_cg.cu k_pcg_stream applies it) --------------
 constexpr uint32_t kMgNone = 0xffffffffu;
 constexpr int kMgMaxLevels = 16;
-constexpr int kMgMaxDistLevels = 3;  // multi-GPU: at most this many leading levels are distributed over the ranks (slab alignment 2^3 columns)
+constexpr int kMgMaxDistLevels = 1;  // multi-GPU: level 0 of the cell hierarchy may be distributed over the ranks (MgDist)
 struct MgLevelPtrs
 {
 	const uint64_t* count;   // occupied cells of this level (device value: the total of the level's rank scan)
@@ -166,11 +166,11 @@ struct MgLevelPtrs
 	uint64_t colstride, dense;
 	uint64_t off_r, off_e0, off_e1;
 };
-// Several ranks (mps_comm.cu, DESIGN.md "multi-GPU"): slabs are cut on cell columns that are multiples of 2^k, so every cell of
-// levels 0 .. k belongs to exactly one rank and a rank's cells are one contiguous range of compact ids at each of those levels.
-// Levels [0, k) are DISTRIBUTED: a rank smooths / restricts / prolongs its own cells and reads the neighbour ranks' halo cells
-// straight from their arenas over NVLink; level k is GATHERED (every rank pulls the other ranks' cells) and levels >= k are
-// replicated: every rank runs them whole, on identical data, with identical results.  k = 0: the whole cycle is replicated.
+// Several ranks (mps_comm.cu, DESIGN.md "multi-GPU"): slabs are cut between cell COLUMNS (all cells of one x index), so every
+// level-0 cell belongs to exactly one rank and a rank's cells are one contiguous range of compact ids.  k = 1: level 0 is
+// DISTRIBUTED — a rank smooths / restricts / prolongs its own cells and reads the neighbour ranks' halo cells straight from their
+// arenas over NVLink — and levels >= 1 are replicated (every rank runs them whole, on identical data, with identical results);
+// k = 0 (few cells): level 0 is gathered from all ranks and the whole cycle is replicated.  mps_cg.cu mg_vcycle.
 struct MgDist
 {
 	int on;                                // 0 on one GPU

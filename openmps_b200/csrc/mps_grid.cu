@@ -338,15 +338,7 @@ cudaError_t sort_and_search(mps_solver* s)
 		const int R = s->comm.nranks;
 		MPS_TRY(s->d_bounds.ensure(4ull * R + 4, st));
 		const uint64_t colstride = env.ncells / static_cast<uint64_t>(env.grid_n[0]);
-		// alignment 2^a columns, a = the number of leading levels of the cell hierarchy that are worth distributing (as mg_ensure
-		// will decide from this step's count; here from the previous step's, or the dense grid on the first step)
-		int a_max = 0;
-		if (s->mg.on)
-		{
-			uint64_t est = s->mg.cells0 ? s->mg.cells0 : env.ncells;
-			while (a_max < kMgMaxDistLevels && est > s->mg.dist_cells) { a_max++; est >>= env.dim; }
-		}
-		if (const char* v = std::getenv("MPS_SLAB_ALIGN")) { const int k = std::atoi(v); if (k >= 0 && k <= kMgMaxDistLevels) a_max = k; }
+		const int a_max = 0; // cuts may fall between any two cell columns (the preconditioner's coarse levels are replicated, MgDist)
 		// work per sorted slot by particle type (scratch: rank[] is free after the scatter, nbr_ptr[] is rebuilt by the search below)
 		uint32_t w[3] = { 8, 4, 1 };
 		if (const char* v = std::getenv("MPS_SLAB_WEIGHTS")) { unsigned a = 0, b = 0, c = 0; if (std::sscanf(v, "%u,%u,%u", &a, &b, &c) == 3 && a + b + c > 0) { w[0] = a; w[1] = b; w[2] = c; } }
@@ -361,7 +353,6 @@ cudaError_t sort_and_search(mps_solver* s)
 		s->own_b.assign(hb.begin(), hb.begin() + R + 1);
 		s->col_b.resize(R + 1);
 		for (int r = 0; r <= R; r++) s->col_b[r] = static_cast<uint32_t>(hb[R + 1 + r]);
-		s->slab_align = static_cast<int>(hb[2 * R + 2]);
 		s->halo_lo.assign(hb.begin() + 2 * R + 4, hb.begin() + 3 * R + 4);
 		s->halo_hi.assign(hb.begin() + 3 * R + 4, hb.begin() + 4 * R + 4);
 		s->own_n = n;

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_mg_cstart(uint64_t bound, const ui
 
 // level-0 operator: S[c][s] = sum over the ACTIVE rows of cell c of the per-row stencil sums written by k_ppe_fill
 // (row_s[s * stride + (row - row0)], rows [row0, row0 + stride) = this rank's); fixed order => run-to-run identical.  Cells of
-// other ranks get 0 (several ranks: their operators are summed in at the gathered level, k_mg_mask + all-reduce).
+// other ranks get 0 (several ranks: the all-reduce of the first replicated level sums the ranks' parts, setup()).
 template<int D>
 __global__ void __launch_bounds__(kThreads) k_mg_s0(uint64_t bound, const uint64_t* __restrict__ count, const uint64_t* __restrict__ cstart,
 	const uint32_t* __restrict__ row_len, const double* __restrict__ row_s, uint64_t stride, uint64_t row0, double* __restrict__ S, double* __restrict__ dinv, double omega)
@@ -215,20 +215,7 @@ __global__ void __launch_bounds__(kThreads) k_mg_galerkin(uint64_t bound, const 
 	dinv_hi[C] = (acc[K / 2] != 0.0) ? omega / acc[K / 2] : 0.0;
 }
 
-// several ranks: before level k's operator is summed over the ranks, everything outside this rank's own cells becomes zero
-// (x + 0 is exact in any order: every rank ends up with bit-identical stencils)
-__global__ void __launch_bounds__(kThreads) k_mg_mask(uint64_t bound, int K, const uint64_t* __restrict__ ranktab, uint64_t colstride, uint64_t dense, int level,
-	uint32_t col_lo, uint32_t col_hi, double* __restrict__ S)
-{
-	const uint64_t t = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-	if (t >= bound * K) return;
-	uint64_t ilo = static_cast<uint64_t>(col_lo >> level) * colstride, ihi = static_cast<uint64_t>(col_hi >> level) * colstride;
-	if (ilo > dense) ilo = dense;
-	if (ihi > dense) ihi = dense;
-	const uint64_t lo = ranktab[ilo], hi = ranktab[ihi];
-	const uint64_t c = t / K;
-	if (c < lo || c >= hi) S[t] = 0.0;
-}
+// several ranks: the damped inverse diagonal of a level whose operator has just been summed over the ranks
 __global__ void __launch_bounds__(kThreads) k_mg_dinv(uint64_t bound, int K, const double* __restrict__ S, double* __restrict__ dinv, double omega)
 {
 	const uint64_t c = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
@@ -295,15 +282,13 @@ cudaError_t setup(mps_solver* s)
 		MgLevelBufs& lo = mg.lv[l];
 		if (s->comm.on && l == mg.k_dist)
 		{
-			// Several ranks: up to here every rank holds the operators of its own cells only (its rows, its children).  Level k is
-			// summed over the ranks (exact: one non-zero contribution per entry) and everything above is rebuilt from it, whole and
-			// identical on every rank.
-			const uint64_t colstride = lo.dense / static_cast<uint64_t>(lo.dims[0]);
-			k_mg_mask<<<blocks_for(lo.bound * K, kThreads), kThreads, 0, st>>>(lo.bound, K, lo.rank.p, colstride, lo.dense, l, s->col_b[s->comm.rank],
-				s->col_b[s->comm.rank + 1], lo.S.p);
+			// Several ranks: up to here every rank holds the operators of its own cells only — k_mg_s0 leaves zeros for the rows of
+			// other ranks, and the Galerkin sums of zeros are zeros — so the sum over the ranks is the whole operator of level k
+			// (a level-1 cell whose children sit on two ranks gets its two partial sums: a + b in either order is the same double).
+			// Everything above is rebuilt from it, whole and identical on every rank.
 			MPS_TRY(comm_allreduce_sum(s, lo.S.p, lo.bound * K));
 			k_mg_dinv<<<blocks_for(lo.bound, kThreads), kThreads, 0, st>>>(lo.bound, K, lo.S.p, lo.dinv.p, mg.omega);
-			L += 2;
+			L += 1;
 		}
 		if (l + 1 == mg.levels) break;
 		MgLevelBufs& hi = mg.lv[l + 1];
@@ -390,13 +375,9 @@ cudaError_t mg_ensure(mps_solver* s, uint64_t cells0)
 	if (mg.in_arena)
 	{
 		// several ranks: the level vectors live in the peer arena, at the same offsets on every rank (the bounds follow from cells0,
-		// which every rank computes from the same replicated state).  Which levels are distributed: those estimated (cells0 / 2^(D l))
-		// to hold more than dist_cells cells, at most as many as the slab alignment of this step allows.
+		// which every rank computes from the same replicated state).  Level 0 is distributed when it holds more than dist_cells cells.
 		MPS_TRY(comm_ensure_arena(s, s->n + 64, mg.vec_total));
-		int k = 0;
-		uint64_t est = cells0;
-		while (k < s->slab_align && k < kMgMaxDistLevels && k + 1 < mg.levels && est > mg.dist_cells) { k++; est >>= s->env.dim; }
-		mg.k_dist = k;
+		mg.k_dist = (cells0 > mg.dist_cells && mg.levels > 1) ? 1 : 0;
 	}
 	MPS_TRY(mg.crow.ensure(s->n + 64, st)); MPS_TRY(mg.cstart.ensure(cells0 + 2, st));
 	MPS_TRY(mg.dinv0.ensure(s->n + 64, st));

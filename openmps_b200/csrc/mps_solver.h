@@ -121,8 +121,8 @@ struct MgBuffers
 	// several ranks: the level vectors r / e0 / e1 live in the "mg" section of the peer arena (same layout on every rank) so that
 	// neighbour ranks can read halo cells; MgLevelBufs::r / e0 / e1 are then unused
 	bool in_arena = false;
-	int k_dist = 0;                  // levels [0, k_dist) distributed, level k_dist gathered, the rest replicated (MgDist)
-	uint64_t dist_cells = 150000;    // a level is distributed when it is estimated to hold more cells than this (MPS_MG_DIST_CELLS)
+	int k_dist = 0;                  // 1: level 0 distributed over the ranks, the rest replicated; 0: everything replicated (MgDist)
+	uint64_t dist_cells = 150000;    // level 0 is distributed when it holds more cells than this (MPS_MG_DIST_CELLS)
 	uint64_t vec_off[kMgMaxLevels][3] = {}; // r, e0, e1 of each level inside the mg section (doubles)
 	uint64_t vec_total = 0;
 };
@@ -227,16 +227,14 @@ struct mps_solver
 
 	int vec_stride() const { return env.dim == 2 ? 2 : 4; }
 
-	// multi-GPU: rows (slots) this rank computes; the state itself is replicated (DESIGN.md "multi-GPU").  The nominal split is
-	// equal slot counts (mps_partition_range); every sort then moves the boundaries to the nearest boundary between cell COLUMNS
-	// (all cells of one x index; a multiple of 2^slab_align columns) so that every cell — and every block of the preconditioner's
-	// first slab_align levels — belongs to exactly one rank (mps_grid.cu k_slab_bounds).
+	// multi-GPU: rows (slots) this rank computes; the state itself is replicated (DESIGN.md "multi-GPU").  Every sort cuts the
+	// cell-sorted slots into equal shares of modelled work and moves each cut to the nearest boundary between cell COLUMNS (all
+	// cells of one x index), so that every cell belongs to exactly one rank (mps_grid.cu k_slab_bounds).
 	mps::Comm comm;
 	std::vector<uint64_t> own_b;           // [nranks + 1] first slot of every rank's slab (valid while own_n == n)
 	std::vector<uint32_t> col_b;           // [nranks + 1] first cell column of every rank's slab
 	std::vector<uint64_t> halo_lo, halo_hi; // [nranks] slots [halo_lo[r], own_b[r]) and [own_b[r + 1], halo_hi[r]): one cell column either side of slab r
 	uint64_t own_n = ~0ull;
-	int slab_align = 0;                    // slab boundaries are multiples of 2^slab_align cell columns
 	mps::DevBuf<unsigned long long> d_bounds; // device scratch of k_slab_bounds: [own_b | col_b | a | ok | halo_lo | halo_hi]
 	bool slabs_set() const { return comm.on && own_n == n && own_b.size() == static_cast<size_t>(comm.nranks) + 1; }
 	uint64_t nominal(int r) const { const uint64_t m = (n + comm.nranks - 1) / comm.nranks, b = static_cast<uint64_t>(r) * m; return b < n ? b : n; }

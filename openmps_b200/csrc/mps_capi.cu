@@ -207,7 +207,20 @@ int mps_create(const mps_env* env, double eps, int device, mps_handle* out)
 	if (e != cudaSuccess || count == 0)
 		return fail(nullptr, MPS_CUDA_ERROR, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
 	if (device < 0 || device >= count) return fail(nullptr, MPS_BAD_ARG, "bad device index");
-	std::unique_ptr<mps_solver> sp(new (std::nothrow) mps_solver());
+	// every error return below gives back what was created so far (stream, events, the scalar blocks), not only the struct
+	auto discard = [](mps_solver* p)
+	{
+		if (!p) return;
+		if (p->ev0) cudaEventDestroy(p->ev0);
+		if (p->ev1) cudaEventDestroy(p->ev1);
+		if (p->ev_cg0) cudaEventDestroy(p->ev_cg0);
+		if (p->ev_cg1) cudaEventDestroy(p->ev_cg1);
+		if (p->stream) cudaStreamDestroy(p->stream);
+		if (p->d_sc) cudaFree(p->d_sc);
+		if (p->h_sc) cudaFreeHost(p->h_sc);
+		delete p;
+	};
+	std::unique_ptr<mps_solver, decltype(discard)> sp(new (std::nothrow) mps_solver(), discard);
 	mps_solver* s = sp.get();
 	if (!s) return fail(nullptr, MPS_BAD_ARG, "out of host memory");
 	s->device = device;

@@ -1035,6 +1035,8 @@ struct DistCtx
 	uint32_t lo[1];                        // this rank's level-0 cells
 	uint32_t hi[1];
 	const uint32_t* gather;                // [nranks + 1] (shared memory) level-0 cell ranges of every rank
+	const uint32_t* part_lo;               // [nranks] (shared memory) level-1 cells that have children in rank r's slab: [part_lo, part_hi)
+	const uint32_t* part_hi;
 };
 
 template<bool MG>
@@ -1060,10 +1062,11 @@ __device__ __forceinline__ LevelView<MG> level_view(const MgArgs& m, const DistC
 // work, so CTA 0 runs them alone between block barriers while the other CTAs wait at the grid barrier that hands the result back.
 // Several ranks (MG), k = m.dist.k:
 //   k = 1  level 0 is DISTRIBUTED: a rank smooths the cells of its own slab (any cut between cell columns) and reads the halo cells
-//          of the adjacent ranks from their arenas; the restriction to level 1 is two steps — every rank leaves the level-0
-//          residual of its cells in its arena (cross-rank barrier), then EVERY rank sums the children of every level-1 cell, own
-//          ones from L2 and the others straight from their owners over NVLink — so level 1 and everything above is replicated
-//          (computed whole, on identical data, with identical results, exactly as on one GPU) without any alignment of the slabs;
+//          of the adjacent ranks from their arenas; the restriction to level 1 is two steps — every rank sums its own children
+//          into the level-1 cells they belong to and leaves these parts in its arena (cross-rank barrier), then EVERY rank adds up
+//          the parts of all level-1 cells, its own from L2 and the others straight from their owners over NVLink — so level 1
+//          and everything above is replicated (computed whole, on identical data, with identical results, exactly as on one GPU)
+//          without any alignment of the slabs;
 //   k = 0  small problems: level 0 is gathered from all ranks at the start and the whole cycle is replicated.
 // On entry the barrier the caller went through must have been cross-rank.
 template<int D, bool MG>
@@ -1108,14 +1111,44 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 		const bool split = MG && dc.k == 1 && l == 0; // distributed level 0 -> replicated level 1
 		if (split)
 		{
+			// step 1: this rank's share of the restriction — the level-1 cells that have children in its slab, own children only
+			// (a level-1 cell spans two cell columns, so at most two adjacent ranks share it) — into the level's `part` vector
 			const MgLevelPtrs& lo = m.lv[0];
+			const MgLevelPtrs& hi = m.lv[1];
 			const LevelView<MG> ev = level_view<MG>(m, dc, 0, 1, lo.e0);
-			// step 1: residual of this rank's level-0 cells, into e1 (free until the way up)
-			for (uint64_t c = dc.lo[0] + gt; c < dc.hi[0]; c += gs)
-				lo.e1[c] = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
+			const uint64_t c_b = dc.part_lo[m.dist.rank], c_e = dc.part_hi[m.dist.rank];
+			const uint64_t first = gt / CH, step = gs / CH;
+			const unsigned q = threadIdx.x % CH;
+			for (uint64_t C0 = c_b; C0 < c_e; C0 += step) // warp-uniform trip count
+			{
+				const uint64_t C = C0 + first;
+				const bool on = C < c_e;
+				const uint32_t ch = on ? __ldg(hi.child + C * CH + q) : kMgNone;
+				double res = 0.0;
+				if (ch != kMgNone && ch >= dc.lo[0] && ch < dc.hi[0])
+				{
+					const uint64_t c = ch;
+					res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
+				}
+#pragma unroll
+				for (int o = 1; o < CH; o <<= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+				if (on && q == 0) hi.part[C] = res;
+			}
 			pbar();
+			// step 2: every rank assembles the whole level 1 — the parts of the (one or two) ranks that share a cell, in rank order,
+			// own part from L2, the others straight from their owners over NVLink (consecutive cells: coalesced)
+			const uint64_t n1 = *hi.count;
+			for (uint64_t C = gt; C < n1; C += gs)
+			{
+				double sum = 0.0;
+				for (int r = 0; r < m.dist.nranks; r++)
+					if (C >= dc.part_lo[r] && C < dc.part_hi[r])
+						sum += (r == m.dist.rank) ? __ldcg(hi.part + C) : ld_relaxed_sys_f64(m.dist.peer_vec[r] + hi.off_part + C);
+				hi.r[C] = sum;
+				hi.e0[C] = __ldg(hi.dinv + C) * sum;
+			}
 		}
-		if (wide || cta0)
+		else if (wide || cta0)
 		{
 			const MgLevelPtrs& lo = m.lv[l];
 			const MgLevelPtrs& hi = m.lv[l + 1];
@@ -1134,18 +1167,7 @@ __device__ __forceinline__ const double* mg_vcycle(const CgStreamArgs& a, const 
 				if (ch != kMgNone)
 				{
 					const uint64_t c = ch;
-					if (split)
-					{
-						// step 2: the child's residual from whoever owns it (rank boundaries of the level-0 cells in dc.gather)
-						if (c >= dc.lo[0] && c < dc.hi[0]) res = __ldcg(lo.e1 + c);
-						else
-						{
-							int o = 0;
-							while (o + 1 < m.dist.nranks && c >= dc.gather[o + 1]) o++;
-							res = ld_relaxed_sys_f64(m.dist.peer_vec[o] + lo.off_e1 + c);
-						}
-					}
-					else res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
+					res = __ldcg(lo.r + c) - stencil_dot<K, MG>(lo.nbr + c * K, lo.S + c * K, ev);
 				}
 #pragma unroll
 				for (int o = 1; o < CH; o <<= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
@@ -1220,7 +1242,7 @@ template<int LPR, int D, bool MG>
 __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 32, 1) k_pcg_stream(CgStreamArgs a, MgArgs m)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ uint32_t s_gather[kMaxPeerRanks + 1];
+	__shared__ uint32_t s_gather[kMaxPeerRanks + 1], s_part_lo[kMaxPeerRanks], s_part_hi[kMaxPeerRanks];
 	if (*reinterpret_cast<volatile int*>(&a.sc->error) != 0) return; // see k_cg_stream
 	const StreamCta cta = stream_setup<true, MG>(a, smem_raw);
 	const StreamSmem& sm = cta.sm;
@@ -1244,13 +1266,19 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 	// several ranks: this rank's cells of the distributed levels, every rank's cells of the gathered one
 	DistCtx dc;
 	dc.k = MG ? m.dist.k : 0;
-	dc.gather = s_gather;
+	dc.gather = s_gather; dc.part_lo = s_part_lo; dc.part_hi = s_part_hi;
 	dc.lo[0] = 0; dc.hi[0] = 0;
 	if (MG)
 	{
 		dc.lo[0] = level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank]);
 		dc.hi[0] = level_cell_begin(m.lv[0], 0, m.dist.col_b[m.dist.rank + 1]);
 		if (threadIdx.x <= static_cast<unsigned>(m.dist.nranks)) s_gather[threadIdx.x] = level_cell_begin(m.lv[0], 0, m.dist.col_b[threadIdx.x]);
+		if (threadIdx.x < static_cast<unsigned>(m.dist.nranks) && m.levels > 1)
+		{
+			// level-1 cells (pairs of columns) touched by the columns [col_b[r], col_b[r + 1]) of rank r
+			s_part_lo[threadIdx.x] = level_cell_begin(m.lv[1], 1, m.dist.col_b[threadIdx.x]);
+			s_part_hi[threadIdx.x] = level_cell_begin(m.lv[1], 1, m.dist.col_b[threadIdx.x + 1] + 1);
+		}
 		__syncthreads();
 	}
 	// levels in use: up to the first one with few enough cells (device-side counts; the same decision in every CTA); the gathered
@@ -1584,9 +1612,9 @@ cudaError_t launch_pcg(mps_solver* s)
 		MgLevelPtrs& q = m.lv[l];
 		q.count = b.rank.p + b.dense; q.S = b.S.p; q.nbr = b.nbr.p; q.dinv = b.dinv.p; q.child = b.child.p; q.parent = b.parent.p;
 		q.ranktab = b.rank.p; q.colstride = b.dense / static_cast<uint64_t>(b.dims[0]); q.dense = b.dense;
-		q.off_r = g.vec_off[l][0]; q.off_e0 = g.vec_off[l][1]; q.off_e1 = g.vec_off[l][2];
-		if (MG) { q.r = arena_vec + q.off_r; q.e0 = arena_vec + q.off_e0; q.e1 = arena_vec + q.off_e1; }
-		else { q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p; }
+		q.off_r = g.vec_off[l][0]; q.off_e0 = g.vec_off[l][1]; q.off_e1 = g.vec_off[l][2]; q.off_part = g.vec_off[l][3];
+		if (MG) { q.r = arena_vec + q.off_r; q.e0 = arena_vec + q.off_e0; q.e1 = arena_vec + q.off_e1; q.part = arena_vec + q.off_part; }
+		else { q.r = b.r.p; q.e0 = b.e0.p; q.e1 = b.e1.p; q.part = nullptr; }
 	}
 	if (MG)
 	{

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(32) k_chunk_build(uint64_t n, const uint32_t* 
 	const uint64_t* __restrict__ cell_start, EnvConst env, ChunkLimits lim, uint32_t* __restrict__ blk_chunks, uint32_t* __restrict__ blk_bytes,
 	uint32_t* __restrict__ blk_cost, uint32_t* __restrict__ blk_live, const uint64_t* __restrict__ chunk_base, const uint64_t* __restrict__ blob_base,
 	const uint64_t* __restrict__ cost_base, const uint64_t* __restrict__ live_base, ChunkDesc* __restrict__ desc, ChunkDesc* __restrict__ live,
-	uint64_t desc_cap, uint32_t* __restrict__ chunk_of_row, unsigned char* __restrict__ blobs, DevScalars* sc)
+	uint64_t desc_cap, uint32_t* __restrict__ chunk_of_row, unsigned char* __restrict__ blobs, DevScalars* sc, const int skip_empty)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	BlockSmem<D>& sm = *reinterpret_cast<BlockSmem<D>*>(smem_raw);
@@ -115,6 +115,19 @@ __global__ void __launch_bounds__(32) k_chunk_build(uint64_t n, const uint32_t* 
 	const uint32_t nrows = static_cast<uint32_t>((r0 + kBlockRows < n) ? kBlockRows : n - r0);
 	const long long ncells = static_cast<long long>(env.ncells);
 
+	// several ranks: a block without any entry (the other ranks' rows: every rank walks the whole, replicated row range) gets no
+	// chunks at all — nobody reads the descriptors or chunk_of_row of rows without entries, and the serial walk below is the cost
+	if (skip_empty)
+	{
+		uint32_t any = 0;
+#pragma unroll
+		for (int k = 0; k < kRowsPerLane; k++) { const uint32_t lr = lane * kRowsPerLane + k; any |= (lr < nrows) ? row_len[r0 + lr] : 0u; }
+		if (!__any_sync(0xffffffffu, any != 0))
+		{
+			if (!EMIT && lane == 0) { blk_chunks[blk] = 0; blk_bytes[blk] = 0; blk_cost[blk] = 0; blk_live[blk] = 0; }
+			return;
+		}
+	}
 	// ---- 1. stage row lengths and cell keys; distinct cells of the rows that have entries; exclusive prefix of the lengths ----
 	uint32_t run = 0; // exclusive count of distinct cells / of entries before this lane's rows
 	{
@@ -353,14 +366,14 @@ cudaError_t build(mps_solver* s)
 	cg.desc_cap = desc_cap;
 
 	k_chunk_build<D, false><<<grid, 32, smem, st>>>(n, s->row_len.p, s->skey.p, s->cell_start.p, s->env, cg.limits, cg.blk_chunks.p,
-		cg.blk_bytes.p, cg.blk_cost.p, cg.blk_live.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, s->d_sc);
+		cg.blk_bytes.p, cg.blk_cost.p, cg.blk_live.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, s->d_sc, s->comm.on ? 1 : 0);
 	s->stats.kernel_launches += 1;
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_chunks.p, cg.chunk_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_bytes.p, cg.blob_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_cost.p, cg.cost_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	MPS_TRY(launch_exclusive_scan_u32_to_u64(cg.blk_live.p, cg.live_base.p, nblk, s->scan_tmp, st, &s->stats.kernel_launches));
 	k_chunk_build<D, true><<<grid, 32, smem, st>>>(n, s->row_len.p, s->skey.p, s->cell_start.p, s->env, cg.limits, nullptr, nullptr, nullptr, nullptr,
-		cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.live_base.p, cg.desc.p, cg.live.p, desc_cap, cg.chunk_of_row.p, cg.blobs.p, s->d_sc);
+		cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.live_base.p, cg.desc.p, cg.live.p, desc_cap, cg.chunk_of_row.p, cg.blobs.p, s->d_sc, s->comm.on ? 1 : 0);
 	k_chunk_totals<<<1, 1, 0, st>>>(cg.chunk_base.p, cg.blob_base.p, cg.cost_base.p, cg.live_base.p, nblk, s->d_sc);
 	s->stats.kernel_launches += 2;
 	return cudaGetLastError();

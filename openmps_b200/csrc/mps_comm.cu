@@ -378,7 +378,8 @@ __global__ void k_peer_barrier(PeerBarrierArgs a)
 	}
 }
 
-// every rank pulls the other ranks' slabs of up to four fields straight from their memory (8-byte words, coalesced)
+// every rank pulls the other ranks' slabs of up to four fields straight from their memory: 16-byte words (coalesced, four in
+// flight per thread: NVLink wants many outstanding requests), 8-byte ends where a range starts or ends on an odd word
 __global__ void __launch_bounds__(256) k_peer_gather(PeerGatherArgs a)
 {
 	const unsigned long long tid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -390,9 +391,23 @@ __global__ void __launch_bounds__(256) k_peer_gather(PeerGatherArgs a)
 		for (int r = 0; r < a.nranks; r++)
 		{
 			if (r == a.rank) continue;
-			const unsigned long long b = a.lo[r] * w, e = a.hi[r] * w;
+			unsigned long long b = a.lo[r] * w, e = a.hi[r] * w;
+			if (e <= b) continue;
 			const unsigned long long* __restrict__ src = a.src[f][r];
-			for (unsigned long long i = b + tid; i < e; i += nthreads) dst[i] = src[i];
+			// odd ends (the arrays are 16-byte aligned, so word parity = address parity)
+			if (b & 1ull) { if (tid == 0) dst[b] = src[b]; b++; }
+			if (e & 1ull) { if (tid == 0) dst[e - 1] = src[e - 1]; e--; }
+			const ulonglong2* __restrict__ s2 = reinterpret_cast<const ulonglong2*>(src + b);
+			ulonglong2* __restrict__ d2 = reinterpret_cast<ulonglong2*>(dst + b);
+			const unsigned long long m = (e - b) >> 1;
+			for (unsigned long long i = tid; i < m; i += 4 * nthreads)
+			{
+				ulonglong2 v[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) { const unsigned long long j = i + u * nthreads; if (j < m) v[u] = s2[j]; }
+#pragma unroll
+				for (int u = 0; u < 4; u++) { const unsigned long long j = i + u * nthreads; if (j < m) d2[j] = v[u]; }
+			}
 		}
 	}
 }
@@ -454,7 +469,7 @@ cudaError_t comm_allgather_state(mps_solver* s, bool pos, bool vel, bool prs, bo
 		if (nden) add(3, 1);
 		if (a.nfields == 0) return cudaSuccess;
 		MPS_TRY(peer_barrier(s));
-		k_peer_gather<<<2 * s->sm_count, 256, 0, s->stream>>>(a);
+		k_peer_gather<<<4 * s->sm_count, 256, 0, s->stream>>>(a);
 		s->stats.kernel_launches += 1;
 		MPS_TRY(peer_barrier(s));
 		c.peer_gathers += 1;

@@ -160,11 +160,12 @@ struct MgLevelPtrs
 	double* r;               // [cells] restricted residual
 	double* e0;              // [cells] correction, two buffers (Jacobi sweeps ping-pong)
 	double* e1;
+	double* part;            // several ranks, level 1 only: this rank's share of the restriction from the distributed level 0
 	// multi-GPU: dense index -> compact id (the level's rank scan, dense + 1 entries), cells per x column, and where the level's
 	// vectors sit inside the "mg" section of every rank's peer arena (doubles)
 	const uint64_t* ranktab;
 	uint64_t colstride, dense;
-	uint64_t off_r, off_e0, off_e1;
+	uint64_t off_r, off_e0, off_e1, off_part;
 };
 // Several ranks (mps_comm.cu, DESIGN.md "multi-GPU"): slabs are cut between cell COLUMNS (all cells of one x index), so every
 // level-0 cell belongs to exactly one rank and a rank's cells are one contiguous range of compact ids.  k = 1: level 0 is

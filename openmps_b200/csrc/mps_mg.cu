@@ -369,7 +369,7 @@ cudaError_t mg_ensure(mps_solver* s, uint64_t cells0)
 		MPS_TRY(lv.S.ensure(bound * K, st)); MPS_TRY(lv.dinv.ensure(bound, st));
 		if (!mg.in_arena) { MPS_TRY(lv.r.ensure(bound, st)); MPS_TRY(lv.e0.ensure(bound, st)); MPS_TRY(lv.e1.ensure(bound, st)); }
 		const uint64_t pad = (bound + 1) & ~1ull;
-		for (int q = 0; q < 3; q++) { mg.vec_off[l][q] = off; off += pad; }
+		for (int q = 0; q < 4; q++) { mg.vec_off[l][q] = off; off += pad; }
 	}
 	mg.vec_total = off;
 	if (mg.in_arena)

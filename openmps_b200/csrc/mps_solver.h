@@ -123,7 +123,7 @@ struct MgBuffers
 	bool in_arena = false;
 	int k_dist = 0;                  // 1: level 0 distributed over the ranks, the rest replicated; 0: everything replicated (MgDist)
 	uint64_t dist_cells = 150000;    // level 0 is distributed when it holds more cells than this (MPS_MG_DIST_CELLS)
-	uint64_t vec_off[kMgMaxLevels][3] = {}; // r, e0, e1 of each level inside the mg section (doubles)
+	uint64_t vec_off[kMgMaxLevels][4] = {}; // r, e0, e1, part of each level inside the mg section (doubles)
 	uint64_t vec_total = 0;
 };
 

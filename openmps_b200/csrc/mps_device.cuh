@@ -179,6 +179,7 @@ struct MgDist
 	int rank, nranks;
 	uint32_t col_b[kMaxPeerRanks + 1];     // first level-0 cell column of every rank's slab
 	double* peer_vec[kMaxPeerRanks];       // the mg section of every rank's arena ([rank] is local)
+	uint64_t halo_lo, halo_hi;             // slots [halo_lo, own0) and [own1, halo_hi): one cell column of the adjacent ranks (what this rank's matrix windows reach)
 };
 struct MgArgs
 {

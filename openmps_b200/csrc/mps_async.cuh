@@ -75,17 +75,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 		: "memory");
 }
 
-// Ampere-style 16-byte async copy (LDGSTS): cheap to issue (~8 cycles), used for the many short window segments
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint64_t policy)
-{
-	asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(policy) : "memory");
-}
-// one arrival on `bar` (pre-counted at init: .noinc) once all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar)
-{
-	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // orders generic-proxy accesses (ordinary loads/stores, here: other CTAs' global stores made visible by a grid barrier)
 // before subsequent async-proxy accesses (bulk copies) of the executing thread
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }

@@ -487,6 +487,7 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 				const ChunkDesc* d = half + j;
 				if (d->nnz == 0) continue; // warp-uniform
 				const uint32_t s = k % S, use = k / S;
+				uint64_t* const fullbar = &sm.full[s * kGroups + k % kGroups]; // chunk k belongs to consumer group k % kGroups
 				k++;
 				// Copies of one chunk: lane 0 the blob (descriptor header included), lanes 1.. one window range each.  The SM's copy
 				// engine charges ~420 cycles per bulk copy whatever its size (tools/tma_bench.cu), hence as few copies as possible:
@@ -505,7 +506,7 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 					const long long tw0 = a.prof ? clock64() : 0;
 					async::mbar_wait(&sm.empty[s], (use & 1u) ^ 1u);
 					if (a.prof) a.prof[blockIdx.x * 8 + 4] += static_cast<unsigned long long>(clock64() - tw0);
-					async::mbar_arrive_expect_tx(&sm.full[s], d->blob_bytes + d->window * (ITER ? 16u : 8u));
+					async::mbar_arrive_expect_tx(fullbar, d->blob_bytes + d->window * (ITER ? 16u : 8u));
 				}
 				__syncwarp();
 				if (MG && ITER && lane != 0 && bytes)
@@ -518,11 +519,11 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 					double2* wdst = static_cast<double2*>(dst);
 					const uint64_t m0 = rb < lo ? (re < lo ? re : lo) : rb; // [rb, m0) left neighbour
 					const uint64_t m1 = re > hi ? (rb > hi ? rb : hi) : re; // [m1, re) right neighbour
-					if (m0 > rb) async::bulk_g2s(wdst, nbz[0] + rb, static_cast<uint32_t>(m0 - rb) * 16u, &sm.full[s], pol_vector);
-					if (m1 > m0) async::bulk_g2s(wdst + (m0 - rb), zprev + m0, static_cast<uint32_t>(m1 - m0) * 16u, &sm.full[s], pol_vector);
-					if (re > m1) async::bulk_g2s(wdst + (m1 - rb), nbz[1] + m1, static_cast<uint32_t>(re - m1) * 16u, &sm.full[s], pol_vector);
+					if (m0 > rb) async::bulk_g2s(wdst, nbz[0] + rb, static_cast<uint32_t>(m0 - rb) * 16u, fullbar, pol_vector);
+					if (m1 > m0) async::bulk_g2s(wdst + (m0 - rb), zprev + m0, static_cast<uint32_t>(m1 - m0) * 16u, fullbar, pol_vector);
+					if (re > m1) async::bulk_g2s(wdst + (m1 - rb), nbz[1] + m1, static_cast<uint32_t>(re - m1) * 16u, fullbar, pol_vector);
 				}
-				else if (bytes) async::bulk_g2s(dst, src, bytes, &sm.full[s], lane == 0 ? pol_matrix : pol_vector);
+				else if (bytes) async::bulk_g2s(dst, src, bytes, fullbar, lane == 0 ? pol_matrix : pol_vector);
 			}
 			__syncwarp(); // every lane is done reading this half
 			if (lane == 0 && bidx + 2 < nbatch) fetch_batch(bidx + 2, seq + 2);
@@ -538,12 +539,17 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 		const unsigned group = warp / gwarps;
 		const unsigned ctid = threadIdx.x - group * gwarps * 32, nct = gwarps * 32;
 		const uint32_t lr = ctid / LPR, sl = ctid % LPR;
-		for (uint32_t q = group; q < live; q += kGroups)
+		// Chunk k (counted over all phases of the solve) sits in stage k % S and belongs to group k % kGroups.  A group must meet the
+		// phases of a barrier it waits on ONE BY ONE (a parity wait cannot tell phase n from phase n + 2), and with an odd S
+		// consecutive uses of a stage alternate between the groups — so every (stage, group) pair has a "full" barrier of its own:
+		// the pair recurs every P = lcm(S, kGroups) chunks, its use number is k / P.
+		const uint32_t P = (S % kGroups == 0) ? S : S * kGroups;
+		for (uint32_t q = (group + kGroups - it % kGroups) % kGroups; q < live; q += kGroups)
 		{
 			const uint32_t k = it + q;
-			const uint32_t s = k % S, use = k / S;
+			const uint32_t s = k % S;
 			const long long tw0 = (a.prof && threadIdx.x == 0) ? clock64() : 0;
-			async::mbar_wait(&sm.full[s], use & 1u);
+			async::mbar_wait(&sm.full[s * kGroups + group], (k / P) & 1u);
 			if (a.prof && threadIdx.x == 0) { a.prof[blockIdx.x * 8 + 1] += static_cast<unsigned long long>(clock64() - tw0); a.prof[blockIdx.x * 8 + 5] += 1; }
 			const ChunkDesc* d = sm.desc(s);
 			const uint32_t row_begin = d->row_begin, rows = d->rows, nnz_pad = round_up8(d->nnz), window = d->window;
@@ -641,8 +647,8 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 	sm.window_stage = a.window_stage;
 	sm.stage_bytes = a.blob_stage_bytes + 24u * a.window_stage;
 	sm.dring = reinterpret_cast<ChunkDesc*>(smem_raw + static_cast<size_t>(S) * sm.stage_bytes);
-	sm.full = reinterpret_cast<uint64_t*>(sm.dring + 2 * kDescBatch);
-	sm.empty = sm.full + S;
+	sm.full = reinterpret_cast<uint64_t*>(sm.dring + 2 * kDescBatch); // [S][kGroups]
+	sm.empty = sm.full + S * kGroups;
 	sm.dfull = sm.empty + S;
 	c.red = reinterpret_cast<double*>(sm.dfull + 2);                          // kMaxStreamWarps + 1
 	uint64_t* ctl64 = reinterpret_cast<uint64_t*>(c.red + kMaxStreamWarps + 1); // row0, row1, zero0, zero1
@@ -651,7 +657,8 @@ __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigne
 	const unsigned nblocks = gridDim.x;
 	if (threadIdx.x == 0)
 	{
-		for (uint32_t s = 0; s < S; s++) { async::mbar_init(&sm.full[s], 1u); async::mbar_init(&sm.empty[s], cwarps / kGroups); }
+		for (uint32_t s = 0; s < S * kGroups; s++) async::mbar_init(&sm.full[s], 1u);
+		for (uint32_t s = 0; s < S; s++) async::mbar_init(&sm.empty[s], cwarps / kGroups);
 		async::mbar_init(&sm.dfull[0], 1u); async::mbar_init(&sm.dfull[1], 1u);
 		async::mbar_init_fence();
 		// this CTA's run of the chunks that have entries: split the modelled cost evenly (descriptors hold its exclusive prefix).
@@ -1524,7 +1531,7 @@ StreamGeometry stream_geometry(const ChunkLimits& lim)
 	g.blob_stage_bytes = round_up(chunk_blob_bytes(lim.max_rows, lim.max_nnz), 128);
 	g.window_stage = round_up(lim.max_window, 16);
 	g.stage_bytes = g.blob_stage_bytes + 24u * g.window_stage;
-	g.fixed_bytes = 2u * kDescBatch * sizeof(ChunkDesc) + 2u * 8u * 8u /* barriers, <= 8 stages */ + 16u + (kMaxStreamWarps + 1) * 8u + 32u + 16u;
+	g.fixed_bytes = 2u * kDescBatch * sizeof(ChunkDesc) + (kGroups + 1u) * 8u * 8u /* barriers, <= 8 stages */ + 16u + (kMaxStreamWarps + 1) * 8u + 32u + 16u;
 	return g;
 }
 
@@ -1865,10 +1872,9 @@ cudaError_t cg_configure(mps_solver* s)
 	const size_t budget = 225u * 1024u;
 	int stages = static_cast<int>((budget - g.fixed_bytes) / g.stage_bytes);
 	if (stages > 8) stages = 8;
+	if (D == 2 && stages > 4) stages = 4; // measured on B200, 1 M particles: 5 stages 7.42 ms per solve, 4 stages 7.05 ms (more look-ahead, more L2 thrash)
 	if (const char* v = std::getenv("MPS_CG_STAGES")) { const int w = std::atoi(v); if (w >= 2 && w <= stages) stages = w; }
-	// every stage must always serve the same consumer group: a group may only wait on barriers it consumes in order
-	// (an mbarrier parity wait cannot tell phase n from phase n + 2)
-	stages = stages / static_cast<int>(kGroups) * static_cast<int>(kGroups);
+	// any depth >= 2 works, odd ones included: every (stage, consumer group) pair has its own "full" barrier (spmv_phase)
 	c.stages = stages;
 	// u16 row offsets / columns and the shared memory of one SM bound what can be streamed; otherwise the generic kernel
 	c.chunked = (lim.max_nnz < 65536u) && (lim.max_window < 65536u) && (stages >= 2);

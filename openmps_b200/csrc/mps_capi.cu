@@ -243,6 +243,14 @@ int mps_create(const mps_env* env, double eps, int device, mps_handle* out)
 	c.r_e = r_eByl_0 * l_0;
 	c.r_e2 = c.r_e * c.r_e;
 	c.neighbor_length = r_eByl_0 * l_0 * (1 + courant * 2);
+	{
+		// exact threshold of the search predicate (Computer.hpp:743: R(x_i, x_j) < neighborLength) in terms of the squared distance
+		volatile double t = c.neighbor_length * c.neighbor_length;
+		auto root = [](double v) { volatile double r = std::sqrt(v); return r; };
+		while (t > 0 && root(t) >= c.neighbor_length) t = std::nextafter(t, 0.0);
+		while (root(t) < c.neighbor_length) t = std::nextafter(t, HUGE_VAL);
+		c.nl2_lim = t;
+	}
 	c.rho = env->rho; c.nu = env->nu; c.eps = eps;
 	for (int k = 0; k < 3; k++) { c.g[k] = 0.0; c.min_x[k] = 0.0; c.max_x[k] = 0.0; c.grid_n[k] = 1; }
 	c.g[D - 1] = -env->g;

@@ -33,6 +33,8 @@ struct EnvConst
 	int dim;
 	int central_gravity;
 	double n0, max_dt, max_dx, l0, r_e, r_e2, neighbor_length, rho, nu, eps;
+	double nl2_lim;   // the smallest double whose (correctly rounded) square root is >= neighbor_length:
+	                  // sqrt(r2) < neighbor_length  <=>  r2 < nl2_lim  for every r2 (sqrt is monotonic), so the search needs no sqrt
 	double g[3];      // Environment::G
 	double min_x[3];
 	double max_x[3];

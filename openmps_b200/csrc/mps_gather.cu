@@ -59,51 +59,73 @@ struct Lists
 	const uint32_t* idx;
 };
 
-// Computer.hpp:618-695.  func(j, x_j, u_j, p_j, type_j) -> contribution; j = -1 denotes the SPP virtual particle
-// (type Fluid, position x_spp, velocity u_i, pressure 0).  Fields a stage does not use are not loaded (NEED_* flags).
+// Walks the neighbour list of slot i in list order and calls visit(j, x_j, dx = x_j - x_i, r2 = dx.dx) for the entries with
+// r2 < r_e2.  kBatch entries at a time: the indices of a batch, then their positions, are loaded side by side — independent
+// L2 round trips instead of a chain of two per entry (ncu, profiles/r02a_ncu_full_gather_kernels_3d1m.txt: these kernels stall
+// on exactly that chain) — before the batch is visited in order.  Past the end of the list the last entry is loaded again
+// and not visited.
+constexpr int kBatch = 4;
+template<int D, typename VISIT>
+__device__ __forceinline__ void walk_in_range(const uint64_t i, const Vec<D>& xi, const Particles<D>& P, const Lists& L, const double r_e2, VISIT visit)
+{
+	const uint64_t eb = L.ptr[i], ee = L.ptr[i + 1];
+	for (uint64_t e0 = eb; e0 < ee; e0 += kBatch)
+	{
+		uint32_t j[kBatch];
+		Vec<D> xj[kBatch];
+#pragma unroll
+		for (int u = 0; u < kBatch; u++) { const uint64_t e = e0 + u; j[u] = L.idx[e < ee ? e : ee - 1]; } // the list never contains i itself nor Disabled particles
+#pragma unroll
+		for (int u = 0; u < kBatch; u++) xj[u] = P.pos[j[u]];
+#pragma unroll
+		for (int u = 0; u < kBatch; u++)
+		{
+			const Acc<D> dx = sub<D>(xj[u], xi);
+			const double r2 = inner<D>(dx, dx);
+			if ((e0 + u < ee) && (r2 < r_e2)) visit(j[u], xj[u], dx, r2);
+		}
+	}
+}
+
+// Computer.hpp:618-695.  func(j, x_j, u_j, p_j, type_j, dx = x_j - x_i, r = |dx|) -> contribution; j = -1 denotes the SPP
+// virtual particle (type Fluid, position x_spp, velocity u_i, pressure 0).  Fields a stage does not use are not loaded
+// (NEED_* flags).  r is evaluated once per pair (the reference's R(), its W() and its norm_2(dx) all round the same
+// sqrt(dx.dx)); the weighted centroid dx_g only feeds the SPP branch, so it is only accumulated for particles below n0.
 template<int D, bool NEED_U, bool NEED_P, bool NEED_T, typename SUM, typename FUNC>
 __device__ __forceinline__ SUM accumulate(const uint64_t i, const Particles<D>& P, const Lists& L, const double* __restrict__ nws,
 	const EnvConst& env, SUM sum, FUNC func)
 {
 	const double r_e = env.r_e;
-	const double r_e2 = env.r_e2;
+	const double n0 = env.n0;
+	const double this_n = nws[i];
+	const bool spp = this_n < n0;
 	Acc<D> dx_g = azero<D>();
 	const Vec<D> xi = P.pos[i];
-	const uint64_t eb = L.ptr[i], ee = L.ptr[i + 1];
-	for (uint64_t e = eb; e < ee; e++)
-	{
-		const uint32_t j = L.idx[e]; // the list never contains i itself nor Disabled particles
-		const Vec<D> xj = P.pos[j];
-		const Acc<D> dx = sub<D>(xj, xi);
-		const double r2 = inner<D>(dx, dx);
-		if (r2 < r_e2)
+	walk_in_range<D>(i, xi, P, L, env.r_e2, [&](const uint32_t j, const Vec<D>& xj, const Acc<D>& dx, const double r2)
 		{
 			const Vec<D> uj = NEED_U ? P.vel[j] : vzero<D>();
 			const double pj = NEED_P ? P.prs[j] : 0.0;
 			const uint8_t tj = NEED_T ? P.type[j] : static_cast<uint8_t>(kFluid);
-			add_to(sum, func(static_cast<long long>(j), xj, uj, pj, tj));
-			add_to(dx_g, scale<D>(weight(sqrt(r2), r_e), dx));
-		}
-	}
+			const double r = sqrt(r2);
+			add_to(sum, func(static_cast<long long>(j), xj, uj, pj, tj, dx, r));
+			if (spp) add_to(dx_g, scale<D>(weight(r, r_e), dx));
+		});
 	// SPP virtual particle, Computer.hpp:664-692
+	if (spp)
 	{
-		const double n0 = env.n0;
-		const double this_n = nws[i];
 #pragma unroll
 		for (int k = 0; k < D; k++) dx_g.v[k] = dx_g.v[k] / n0;
-		if (this_n < n0)
+		const double r_g = sqrt(inner<D>(dx_g, dx_g));
+		if (r_g > DBL_EPSILON)
 		{
-			const double r_g = sqrt(inner<D>(dx_g, dx_g));
-			if (r_g > DBL_EPSILON)
-			{
-				const double w_spp = n0 - this_n;
-				const double r_spp = r_e / (w_spp + 1);
-				const double f = r_spp / r_g;
-				Vec<D> x_spp = vzero<D>();
+			const double w_spp = n0 - this_n;
+			const double r_spp = r_e / (w_spp + 1);
+			const double f = r_spp / r_g;
+			Vec<D> x_spp = vzero<D>();
 #pragma unroll
-				for (int k = 0; k < D; k++) x_spp.v[k] = xi.v[k] - f * dx_g.v[k];
-				add_to(sum, func(-1LL, x_spp, P.vel[i], 0.0, static_cast<uint8_t>(kFluid)));
-			}
+			for (int k = 0; k < D; k++) x_spp.v[k] = xi.v[k] - f * dx_g.v[k];
+			const Acc<D> dxs = sub<D>(x_spp, xi);
+			add_to(sum, func(-1LL, x_spp, P.vel[i], 0.0, static_cast<uint8_t>(kFluid), dxs, sqrt(inner<D>(dxs, dxs))));
 		}
 	}
 	return sum;
@@ -131,23 +153,15 @@ __global__ void __launch_bounds__(kThreads) k_density(uint64_t first, uint64_t n
 	if ((t != kDummy) && (t != kDisabled))
 	{
 		// nWithoutSpp[i] = n0 while accumulating => the SPP branch is inactive (Computer.hpp:800); done inline here
-		const double r_e = env.r_e, r_e2 = env.r_e2;
+		const double r_e = env.r_e;
 		const Vec<D> xi = P.pos[i];
 		double sum = 0.0;
 		uint32_t len = 1;
-		const uint64_t eb = L.ptr[i], ee = L.ptr[i + 1];
-		for (uint64_t e = eb; e < ee; e++)
-		{
-			const uint32_t j = L.idx[e];
-			const Vec<D> xj = P.pos[j];
-			const Acc<D> dx = sub<D>(xj, xi);
-			const double r2 = inner<D>(dx, dx);
-			if (r2 < r_e2)
+		walk_in_range<D>(i, xi, P, L, env.r_e2, [&](const uint32_t j, const Vec<D>&, const Acc<D>&, const double r2)
 			{
-				sum += weight(dist<D>(xi, xj), r_e);
+				sum += weight(sqrt(r2), r_e);
 				if (COUNT_ROWS) len += (P.type[j] != kDummy) ? 1u : 0u;
-			}
-		}
+			});
 		nws[i] = sum;
 		P.nden[i] = (sum < n0) ? n0 : sum; // std::max(thisN, n0)
 		if (COUNT_ROWS) { row_len[i] = len; x0[i] = xi; }
@@ -164,14 +178,12 @@ template<int D>
 __device__ __forceinline__ double dndt(const uint64_t i, const Particles<D>& P, const Lists& L, const double* __restrict__ nws, const EnvConst& env)
 {
 	if (nws[i] < env.n0) return 0.0;
-	const Vec<D> xi = P.pos[i], ui = P.vel[i];
+	const Vec<D> ui = P.vel[i];
 	const double s = accumulate<D, true, false, false>(i, P, L, nws, env, 0.0,
-		[&](long long, const Vec<D>& x, const Vec<D>& u, double, uint8_t) -> double
+		[&](long long, const Vec<D>&, const Vec<D>& u, double, uint8_t, const Acc<D>& dx, const double r) -> double
 		{
-			const Acc<D> dx = sub<D>(x, xi);
 			const Acc<D> duv = sub<D>(u, ui);
-			const double r = sqrt(inner<D>(dx, dx)); // norm_2(dx): |dx_k| * |dx_k| == dx_k * dx_k
-			return inner<D>(dx, duv) / (r * r * r);
+			return inner<D>(dx, duv) / (r * r * r); // r = norm_2(dx): |dx_k| * |dx_k| == dx_k * dx_k
 		});
 	return -env.r_e * s;
 }
@@ -211,13 +223,9 @@ __global__ void __launch_bounds__(kThreads) k_explicit_accel(uint64_t first, uin
 	if (P.type[i] != kFluid) return;
 	const Vec<D> xi = P.pos[i], ui = P.vel[i];
 	Acc<D> vis = accumulate<D, true, false, true>(i, P, L, nws, env, azero<D>(),
-		[&](long long, const Vec<D>& x, const Vec<D>& u, double, uint8_t type) -> Acc<D>
+		[&](long long, const Vec<D>&, const Vec<D>& u, double, uint8_t type, const Acc<D>&, const double r) -> Acc<D>
 		{
-			if (type != kDummy)
-			{
-				const double r = dist<D>(xi, x);
-				return scale<D>(env.visc_coef / (r * r * r), sub<D>(u, ui));
-			}
+			if (type != kDummy) return scale<D>(env.visc_coef / (r * r * r), sub<D>(u, ui)); // r = R(x_i, x_j)
 			return azero<D>();
 		});
 	if (env.central_gravity)
@@ -359,11 +367,6 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 	atomicAdd(&sc->active_rows, 1ull); // same address for the whole warp: aggregated by the compiler into one atomic
 	const double dt = sc->dt;
 	const double n0 = env.n0;
-	// right-hand side, Computer.hpp:1204-1214
-	const double speed = dndt<D>(i, P, L, nws, env);
-	b[i] = -env.rho / (n0 * dt) * (speed + ecs[i]);
-	x[i] = P.prs[i];
-
 	// where this row's entries go
 	uint32_t* col = nullptr; double* val = nullptr; uint16_t* lcol = nullptr;
 	uint64_t w = 0;
@@ -405,20 +408,54 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 		}
 	};
 
-	// matrix row, Computer.hpp:1246-1327
-	const Vec<D> xi = P.pos[i];
-	const double a_ii = accumulate<D, false, false, true>(i, P, L, nws, env, 0.0,
-		[&](long long j, const Vec<D>& xj, const Vec<D>&, double, uint8_t type) -> double
+	// ONE walk of the list for the right-hand side (Computer.hpp:1204-1214: Dn/Dt, Computer.hpp:838-872) and the matrix row
+	// (Computer.hpp:1246-1327): both are sums over the same in-range pairs, each kept in its own reference order.  Dn/Dt is zero
+	// for particles below n0 (Computer.hpp:845) and the SPP virtual particle (Computer.hpp:664-692) exists only for those, so
+	// a particle needs either the velocity differences or the weighted centroid, never both.
+	const Vec<D> xi = P.pos[i], ui = P.vel[i];
+	const double r_e = env.r_e;
+	const double this_n = nws[i];
+	const bool spp = this_n < n0;
+	double s_dn = 0.0, a_ii = 0.0;
+	Acc<D> dx_g = azero<D>();
+	walk_in_range<D>(i, xi, P, L, env.r_e2, [&](const uint32_t j, const Vec<D>&, const Acc<D>& dx, const double r2)
 		{
-			if (type != kDummy)
+			const uint8_t tj = P.type[j];
+			const double r = sqrt(r2);
+			const double r3 = r * r * r;
+			if (!spp)
 			{
-				const double r = dist<D>(xi, xj);
-				const double a_ij = env.ppe_coef / (r * r * r);
-				if (j >= 0) put(static_cast<uint32_t>(j), a_ij);
-				return -a_ij;
+				const Acc<D> duv = sub<D>(P.vel[j], ui);
+				s_dn += inner<D>(dx, duv) / r3;
 			}
-			return 0.0;
+			if (tj != kDummy)
+			{
+				const double a_ij = env.ppe_coef / r3;
+				put(j, a_ij);
+				a_ii += -a_ij;
+			}
+			if (spp) add_to(dx_g, scale<D>(weight(r, r_e), dx));
 		});
+	if (spp)
+	{
+#pragma unroll
+		for (int k = 0; k < D; k++) dx_g.v[k] = dx_g.v[k] / n0;
+		const double r_g = sqrt(inner<D>(dx_g, dx_g));
+		if (r_g > DBL_EPSILON)
+		{
+			const double w_spp = n0 - this_n;
+			const double r_spp = r_e / (w_spp + 1);
+			const double f = r_spp / r_g;
+			Vec<D> x_spp = vzero<D>();
+#pragma unroll
+			for (int k = 0; k < D; k++) x_spp.v[k] = xi.v[k] - f * dx_g.v[k];
+			const double r = dist<D>(xi, x_spp);
+			a_ii += -(env.ppe_coef / (r * r * r)); // the virtual particle is a Fluid neighbour without a column
+		}
+	}
+	const double speed = spp ? 0.0 : -r_e * s_dn;
+	b[i] = -env.rho / (n0 * dt) * (speed + ecs[i]);
+	x[i] = P.prs[i];
 	put(static_cast<uint32_t>(i), a_ii);
 	if (PRE)
 	{
@@ -467,13 +504,12 @@ __global__ void __launch_bounds__(kThreads) k_gradient(uint64_t first, uint64_t 
 	const double pi = P.prs[i];
 	const Vec<D> xi = P.pos[i];
 	const Acc<D> s = accumulate<D, false, true, true>(i, P, L, nws, env, azero<D>(),
-		[&](long long, const Vec<D>& x, const Vec<D>&, double p, uint8_t type) -> Acc<D>
+		[&](long long, const Vec<D>&, const Vec<D>&, double p, uint8_t type, const Acc<D>& dx, const double r) -> Acc<D>
 		{
 			if (type != kDummy)
 			{
-				const Acc<D> dx = sub<D>(x, xi);
 				const double r2 = inner<D>(dx, dx);
-				return scale<D>((p + pi) / r2 * weight(sqrt(r2), r_e), dx);
+				return scale<D>((p + pi) / r2 * weight(r, r_e), dx); // r = sqrt(r2)
 			}
 			return azero<D>();
 		});
@@ -513,11 +549,10 @@ __global__ void __launch_bounds__(kThreads) k_ds(uint64_t first, uint64_t n, Par
 	const Vec<D> xi = P.pos[i];
 	const Vec<D> x0i = x0[i];
 	const Acc<D> s = accumulate<D, false, false, true>(i, P, L, nws, env, azero<D>(),
-		[&](long long j, const Vec<D>& x, const Vec<D>&, double, uint8_t type) -> Acc<D>
+		[&](long long j, const Vec<D>&, const Vec<D>&, double, uint8_t type, const Acc<D>& dx, const double) -> Acc<D>
 		{
 			if ((type != kDummy) && (j >= 0))
 			{
-				const Acc<D> dx = sub<D>(x, xi);
 				const double r2 = inner<D>(dx, dx);
 				if (r2 < d2)
 				{

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n,
 	const long long zhi = (c[D - 1] + 1 < nz) ? c[D - 1] + 1 : nz - 1;
 	uint32_t cnt = 0;
 	const uint64_t base = FILL ? nbr_ptr[i] : 0;
+	const double nl2_lim = env.nl2_lim;
 
 	for (int ox = -1; ox <= 1; ox++)
 	{
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n,
 					const double d = xi.v[a] - xj.v[a];
 					r2 += d * d; // -fmad=false: rounded product, then rounded sum, as uBLAS inner_prod
 				}
-				if (sqrt(r2) < env.neighbor_length)
+				if (r2 < nl2_lim) // <=> sqrt(r2) < neighbor_length, bit for bit (EnvConst::nl2_lim)
 				{
 					if (FILL) nbr[base + cnt] = static_cast<uint32_t>(j);
 					cnt++;

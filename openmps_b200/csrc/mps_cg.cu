@@ -231,6 +231,7 @@ struct CgStreamArgs
 	uint32_t window_stage;     // doubles reserved per stage and vector for the window
 	uint32_t stages;
 	int l2_stream;             // blobs do not fit L2: stream them evict_first
+	uint32_t producers;        // producer warps per CTA (the last warps of the block)
 	unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (mps_get_cg_profile), nullptr = off
 	const double* cta_frac;    // [gridDim.x + 1] cumulative cost share of the CTAs (load balance, k_cg_rebalance)
 	unsigned long long* cta_meas; // [2][gridDim.x] {cost taken, SpMV cycles} of this solve, or nullptr
@@ -239,8 +240,12 @@ struct CgStreamArgs
 };
 
 constexpr int kProfStages = 64;     // per-stage counters of the preconditioned solve behind the per-CTA ones (CgBuffers::prof)
-constexpr int kMaxStreamWarps = 17;
-constexpr int kStreamWarps2d = 9;   // 2-D: at most 8 consumer warps + 1 producer warp
+// Warps per CTA = consumer warps + producer warps.  Registers are allocated per SM sub-partition (4 per SM, 16384 each): 17..20
+// warps put 5 on one of them (<= 96 registers per thread), 9..12 warps 3 (<= 168) — so up to 4 producer warps come for free
+// next to 16 (3-D) / 8 (2-D) consumer warps.
+constexpr int kMaxProducers = 4;
+constexpr int kMaxStreamWarps = 16 + kMaxProducers;
+constexpr int kStreamWarps2d = 8 + kMaxProducers;   // 2-D: at most 8 consumer warps
 constexpr unsigned kGroups = 2; // consumer groups working on alternate chunks
 constexpr uint32_t kDescBatch = 16; // descriptors per half of the producer's descriptor ring
 
@@ -447,34 +452,42 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 	const uint64_t pol_matrix, const uint64_t pol_vector)
 {
 	const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const unsigned cwarps = (blockDim.x >> 5) - 1; // consumer warps; the last warp is the producer
+	const unsigned np = a.producers;
+	const unsigned cwarps = (blockDim.x >> 5) - np; // consumer warps; the last np warps are the producers
 	const uint32_t S = a.stages;
 	double local = 0.0;
-	if (warp == cwarps)
+	if (warp >= cwarps)
 	{
-		// ---- producer warp: runs up to S - 1 chunks ahead of the consumers; lanes issue the copies of one chunk in parallel:
-		//      lane 0 descriptor, lane 1 blob, lanes 2.. one window range of one vector each ----
+		// ---- producer warps: run up to S - 1 chunks ahead of the consumers.  A bulk copy holds the issuing WARP for ~560 cycles
+		//      whatever its size, and copies issued by several lanes of one warp go one after the other — but copies issued by
+		//      different warps overlap (tools/tma_bench.cu, "multi": 564 cycles per copy with one issuing warp, 74 with eight).
+		//      So the copies of one chunk (the blob + one per window range: 4 in 2-D, 10 in 3-D) are dealt round-robin to the np
+		//      producer warps: copy c is issued by lane c / np of producer warp c % np.  Every producer warp walks the same chunk
+		//      sequence and waits for the stage to be free itself; warp 0 alone posts the expected bytes (the stage's barrier
+		//      cannot complete before that: its one pending arrival is that post). ----
+		const unsigned pw = warp - cwarps;
 		if (lane == 0) async::fence_proxy_async(); // other CTAs' stores (made visible by the grid barrier) before our async-proxy reads
 		__syncwarp();
 		// The descriptors of this CTA's chunks are themselves streamed through a small double-buffered shared-memory ring
-		// (kDescBatch per half): under full memory load an ordinary global load takes thousands of cycles, and the producer
+		// (kDescBatch per half): under full memory load an ordinary global load takes thousands of cycles, and the producers
 		// must never wait for one.
 		uint32_t k = it;
 		const uint32_t nbatch = (c1 - c0 + kDescBatch - 1) / kDescBatch;
 		auto fetch_batch = [&](const uint32_t bidx, const uint32_t seq)
 		{
-			// lane 0 only
+			// producer warp 0, lane 0 only
 			const uint32_t first = c0 + bidx * kDescBatch;
 			const uint32_t count = (c1 - first < kDescBatch) ? (c1 - first) : kDescBatch;
 			const uint32_t bytes = count * static_cast<uint32_t>(sizeof(ChunkDesc));
 			async::mbar_arrive_expect_tx(&sm.dfull[seq & 1u], bytes);
 			async::bulk_g2s(sm.dring + (seq & 1u) * kDescBatch, a.desc + first, bytes, &sm.dfull[seq & 1u], pol_vector);
 		};
-		if (lane == 0)
+		if (pw == 0 && lane == 0)
 		{
 			if (nbatch > 0) fetch_batch(0, dseq);
 			if (nbatch > 1) fetch_batch(1, dseq + 1);
 		}
+		const uint32_t cidx = pw + lane * np; // this lane's copy of every chunk: 0 the blob, 1.. window range cidx - 1
 		for (uint32_t bidx = 0; bidx < nbatch; bidx++)
 		{
 			const uint32_t seq = dseq + bidx;
@@ -489,33 +502,31 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 				const uint32_t s = k % S, use = k / S;
 				uint64_t* const fullbar = &sm.full[s * kGroups + k % kGroups]; // chunk k belongs to consumer group k % kGroups
 				k++;
-				// Copies of one chunk: lane 0 the blob (descriptor header included), lanes 1.. one window range each.  The SM's copy
-				// engine charges ~420 cycles per bulk copy whatever its size (tools/tma_bench.cu), hence as few copies as possible:
-				// {r, p_prev} travel interleaved.
+				// {r, p_prev} travel interleaved: one copy per window range instead of two
 				const void* src = nullptr; void* dst = nullptr; uint32_t bytes = 0;
-				if (lane == 0) { src = a.blobs + d->blob_off; dst = sm.stage(s); bytes = d->blob_bytes; }
-				else if (lane <= kMaxRanges)
+				if (cidx == 0) { src = a.blobs + d->blob_off; dst = sm.stage(s); bytes = d->blob_bytes; }
+				else if (cidx <= kMaxRanges)
 				{
-					const uint32_t q = lane - 1;
+					const uint32_t q = cidx - 1;
 					const uint32_t len = d->range_len[q]; // 0 for unused ranges
 					if (ITER) { bytes = len * 16u; src = zprev + d->range_start[q]; dst = sm.zwin(s) + d->range_off[q]; }
 					else { bytes = len * 8u; src = a.x + d->range_start[q]; dst = sm.pwin(s) + d->range_off[q]; }
 				}
 				if (lane == 0)
 				{
-					const long long tw0 = a.prof ? clock64() : 0;
+					const long long tw0 = (a.prof && pw == 0) ? clock64() : 0;
 					async::mbar_wait(&sm.empty[s], (use & 1u) ^ 1u);
-					if (a.prof) a.prof[blockIdx.x * 8 + 4] += static_cast<unsigned long long>(clock64() - tw0);
-					async::mbar_arrive_expect_tx(fullbar, d->blob_bytes + d->window * (ITER ? 16u : 8u));
+					if (a.prof && pw == 0) a.prof[blockIdx.x * 8 + 4] += static_cast<unsigned long long>(clock64() - tw0);
+					if (pw == 0) async::mbar_arrive_expect_tx(fullbar, d->blob_bytes + d->window * (ITER ? 16u : 8u));
 				}
 				__syncwarp();
-				if (MG && ITER && lane != 0 && bytes)
+				if (MG && ITER && cidx != 0 && bytes)
 				{
 					// multi-GPU: slots below own0 / from own1 on live in the left / right neighbour's buffer (same index, its memory)
 					const PeerLink& pl = a.peer;
 					const double2* nbz[2] = { (zprev == a.z0) ? pl.nb_z0[0] : pl.nb_z1[0], (zprev == a.z0) ? pl.nb_z0[1] : pl.nb_z1[1] };
 					const uint64_t lo = nbz[0] ? a.own0 : 0ull, hi = nbz[1] ? a.own1 : ~0ull;
-					const uint64_t rb = d->range_start[lane - 1], re = rb + d->range_len[lane - 1];
+					const uint64_t rb = d->range_start[cidx - 1], re = rb + d->range_len[cidx - 1];
 					double2* wdst = static_cast<double2*>(dst);
 					const uint64_t m0 = rb < lo ? (re < lo ? re : lo) : rb; // [rb, m0) left neighbour
 					const uint64_t m1 = re > hi ? (rb > hi ? rb : hi) : re; // [m1, re) right neighbour
@@ -523,10 +534,12 @@ __device__ __forceinline__ double spmv_phase(const CgStreamArgs& a, const Stream
 					if (m1 > m0) async::bulk_g2s(wdst + (m0 - rb), zprev + m0, static_cast<uint32_t>(m1 - m0) * 16u, fullbar, pol_vector);
 					if (re > m1) async::bulk_g2s(wdst + (m1 - rb), nbz[1] + m1, static_cast<uint32_t>(re - m1) * 16u, fullbar, pol_vector);
 				}
-				else if (bytes) async::bulk_g2s(dst, src, bytes, fullbar, lane == 0 ? pol_matrix : pol_vector);
+				else if (bytes) async::bulk_g2s(dst, src, bytes, fullbar, cidx == 0 ? pol_matrix : pol_vector);
 			}
-			__syncwarp(); // every lane is done reading this half
-			if (lane == 0 && bidx + 2 < nbatch) fetch_batch(bidx + 2, seq + 2);
+			// every lane of every producer warp is done reading this half
+			if (np > 1) asm volatile("bar.sync %0, %1;" ::"r"(1u + kGroups), "r"(np * 32u) : "memory");
+			else __syncwarp();
+			if (pw == 0 && lane == 0 && bidx + 2 < nbatch) fetch_batch(bidx + 2, seq + 2);
 		}
 		dseq += nbatch;
 	}
@@ -639,7 +652,7 @@ template<bool ZERO_ROWS, bool MG = false>
 __device__ __forceinline__ StreamCta stream_setup(const CgStreamArgs& a, unsigned char* smem_raw)
 {
 	const uint32_t S = a.stages;
-	const unsigned nthreads = blockDim.x, cwarps = (blockDim.x >> 5) - 1;
+	const unsigned nthreads = blockDim.x, cwarps = (blockDim.x >> 5) - a.producers;
 	StreamCta c;
 	StreamSmem& sm = c.sm;
 	sm.base = smem_raw;
@@ -1548,7 +1561,7 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 	CgBuffers& c = s->cg;
 	const StreamGeometry g = stream_geometry(c.limits);
 	L.smem_bytes = static_cast<size_t>(c.stages) * g.stage_bytes + g.fixed_bytes;
-	L.threads = (c.consumer_warps + 1) * 32;
+	L.threads = (c.consumer_warps + c.producers) * 32;
 	L.grid = static_cast<unsigned>(s->sm_count); // one CTA per SM: the ring wants the whole shared memory
 	cudaError_t e = c.partials.ensure(2ull * L.grid + 8, s->stream);
 	if (e != cudaSuccess) return e;
@@ -1572,6 +1585,7 @@ cudaError_t prepare_stream(mps_solver* s, StreamLaunch& L)
 	a.blob_stage_bytes = g.blob_stage_bytes; a.window_stage = g.window_stage; a.stages = static_cast<uint32_t>(c.stages);
 	// entries <= neighbour entries + rows: stream the matrix past L2 when it cannot stay resident next to the vectors
 	a.l2_stream = ((s->nbr_total + (s->own1() - s->own0())) * 10ull + c.n * 48ull > (96ull << 20)) ? 1 : 0;
+	a.producers = static_cast<uint32_t>(c.producers);
 	a.prof = nullptr;
 	a.cta_frac = c.cta_frac.p; a.cta_meas = nullptr;
 	a.own0 = s->own0(); a.own1 = s->own1();
@@ -1846,9 +1860,12 @@ cudaError_t cg_configure(mps_solver* s)
 	if (const char* v = std::getenv("MPS_CG_WARPS")) warps = std::atoi(v);
 	warps = warps / static_cast<int>(kGroups) * static_cast<int>(kGroups);
 	if (warps < static_cast<int>(kGroups)) warps = kGroups;
-	if (warps > kMaxStreamWarps - 1) warps = kMaxStreamWarps - 1;
-	if (D == 2 && warps > kStreamWarps2d - 1) warps = kStreamWarps2d - 1;
+	if (warps > kMaxStreamWarps - kMaxProducers) warps = kMaxStreamWarps - kMaxProducers;
+	if (D == 2 && warps > kStreamWarps2d - kMaxProducers) warps = kStreamWarps2d - kMaxProducers;
 	c.consumer_warps = warps;
+	// producer warps: one bulk copy occupies its issuing warp for ~560 cycles (tools/tma_bench.cu) and a chunk needs 4 (2-D) / 10 (3-D)
+	c.producers = kMaxProducers;
+	if (const char* v = std::getenv("MPS_CG_PRODUCERS")) { const int w = std::atoi(v); if (w >= 1 && w <= kMaxProducers) c.producers = w; }
 	c.lanes_per_row = (D == 3) ? 4 : 1;
 	if (const char* v = std::getenv("MPS_CG_LPR")) { const int w = std::atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) c.lanes_per_row = w; }
 	ChunkLimits lim;

@@ -98,6 +98,30 @@ __device__ __forceinline__ void window_of(const BlockSmem<D>& sm, const uint32_t
 	for (uint32_t k = 0; k < w.n; k++) w.total += w.len[k];
 }
 
+// the same window, its size only (what the greedy walk needs: registers, no range arrays)
+template<int D>
+__device__ __forceinline__ uint32_t window_total(const BlockSmem<D>& sm, const uint32_t da, const uint32_t db, const EnvConst& env)
+{
+	const long long ncells = static_cast<long long>(env.ncells);
+	const long long c_a = sm.cell[da], c_b = sm.cell[db];
+	uint64_t total = 0, prev_end = 0;
+	bool have = false;
+#pragma unroll
+	for (int k = 0; k < BlockSmem<D>::kCols; k++)
+	{
+		const long long shift = col_shift<D>(k, env);
+		const long long lo = c_a + shift - 1, hi = c_b + shift + 1;
+		if (hi < 0 || lo >= ncells) continue;
+		uint64_t s = sm.cs_lo[da][k], e = sm.cs_hi[db][k];
+		if (e <= s) continue;
+		s &= ~1ull;
+		e = (e + 1) & ~1ull;
+		if (have && s <= prev_end) { if (e > prev_end) { total += e - prev_end; prev_end = e; } }
+		else { total += e - s; prev_end = e; have = true; }
+	}
+	return static_cast<uint32_t>(total);
+}
+
 template<int D, bool EMIT>
 __global__ void __launch_bounds__(32) k_chunk_build(uint64_t n, const uint32_t* __restrict__ row_len, const uint32_t* __restrict__ skey,
 	const uint64_t* __restrict__ cell_start, EnvConst env, ChunkLimits lim, uint32_t* __restrict__ blk_chunks, uint32_t* __restrict__ blk_bytes,
@@ -211,7 +235,7 @@ __global__ void __launch_bounds__(32) k_chunk_build(uint64_t n, const uint32_t* 
 		uint32_t n_chunks = 0, n_live = 0, bytes = 0, cost = 0, err = 0;
 		uint32_t begin = 0, rows = 0, nnz = 0, first_active = 0;
 		int da = -1, db = -1;
-		Window win; win.n = 0; win.total = 0;
+		uint32_t wtotal = 0;
 		auto close = [&]()
 		{
 			sm.ch_begin[n_chunks] = static_cast<uint16_t>(begin);
@@ -227,29 +251,29 @@ __global__ void __launch_bounds__(32) k_chunk_build(uint64_t n, const uint32_t* 
 		{
 			const uint32_t len = sm.row_len[r];
 			int na = da, nb = db;
-			Window nwin = win;
+			uint32_t nwtotal = wtotal;
 			uint32_t nfirst = first_active;
 			if (len > 0)
 			{
 				const int c = sm.dcell[r]; // rows with entries are never Disabled => a real cell
 				if (na < 0) { na = c; nfirst = r; }
-				if (c != nb) { nb = c; window_of<D>(sm, static_cast<uint32_t>(na), static_cast<uint32_t>(nb), env, nwin); }
+				if (c != nb) { nb = c; nwtotal = window_total<D>(sm, static_cast<uint32_t>(na), static_cast<uint32_t>(nb), env); }
 			}
-			const bool fits = (rows + 1 <= lim.max_rows) && (nnz + len <= lim.max_nnz) && (nwin.total <= lim.max_window);
+			const bool fits = (rows + 1 <= lim.max_rows) && (nnz + len <= lim.max_nnz) && (nwtotal <= lim.max_window);
 			if (!fits && rows > 0)
 			{
 				close();
-				begin = r; rows = 0; nnz = 0; na = -1; nb = -1; nwin.n = 0; nwin.total = 0;
+				begin = r; rows = 0; nnz = 0; na = -1; nb = -1; nwtotal = 0;
 				if (len > 0)
 				{
 					na = nb = sm.dcell[r]; nfirst = r;
-					window_of<D>(sm, static_cast<uint32_t>(na), static_cast<uint32_t>(nb), env, nwin);
+					nwtotal = window_total<D>(sm, static_cast<uint32_t>(na), static_cast<uint32_t>(nb), env);
 				}
 				// a single row that does not fit: the host sized the limits from the cell capacity, so this is a logic error
-				if (len > lim.max_nnz || nwin.total > lim.max_window) err = 1;
+				if (len > lim.max_nnz || nwtotal > lim.max_window) err = 1;
 			}
 			else if (!fits) err = 1;
-			rows += 1; nnz += len; da = na; db = nb; win = nwin; first_active = nfirst;
+			rows += 1; nnz += len; da = na; db = nb; wtotal = nwtotal; first_active = nfirst;
 		}
 		if (rows > 0) close();
 		sm.ch_begin[n_chunks] = static_cast<uint16_t>(nrows);

@@ -74,7 +74,8 @@ struct CgBuffers
 	bool chunked = false;    // the assembled system is in chunk-blob form and is solved by the streaming kernel
 	ChunkLimits limits{};
 	int stages = 0;          // shared-memory pipeline depth of the streaming kernel
-	int consumer_warps = 8;  // consumer warps per CTA of the streaming kernel (+ 1 producer warp)
+	int consumer_warps = 8;  // consumer warps per CTA of the streaming kernel
+	int producers = 1;       // + producer warps (issue the bulk copies)
 	int lanes_per_row = 1;   // 1 (2-D: ~21 entries per row) or 4 (3-D: ~57)
 	DevBuf<uint32_t> blk_chunks, blk_bytes, blk_cost, blk_live, chunk_of_row;
 	DevBuf<uint64_t> chunk_base, blob_base, cost_base, live_base;

@@ -174,21 +174,28 @@ __global__ void __launch_bounds__(kThreads) k_search(uint64_t first, uint64_t n,
 			const unsigned long long lin_lo = linear_cell<D>(b, env);
 			const unsigned long long lin_hi = lin_lo + static_cast<unsigned long long>(zhi - zlo);
 			const uint64_t jb = cell_start[lin_lo], je = cell_start[lin_hi + 1];
-			for (uint64_t j = jb; j < je; j++)
+			// four candidates at a time: their positions are loaded side by side (independent requests), then tested in slot order
+			for (uint64_t j0 = jb; j0 < je; j0 += 4)
 			{
-				if (j == i) continue;
-				const Vec<D> xj = pos[j];
-				double r2 = 0.0;
+				Vec<D> xj[4];
 #pragma unroll
-				for (int a = 0; a < D; a++)
+				for (int u = 0; u < 4; u++) { const uint64_t j = j0 + u; xj[u] = pos[j < je ? j : je - 1]; }
+#pragma unroll
+				for (int u = 0; u < 4; u++)
 				{
-					const double d = xi.v[a] - xj.v[a];
-					r2 += d * d; // -fmad=false: rounded product, then rounded sum, as uBLAS inner_prod
-				}
-				if (r2 < nl2_lim) // <=> sqrt(r2) < neighbor_length, bit for bit (EnvConst::nl2_lim)
-				{
-					if (FILL) nbr[base + cnt] = static_cast<uint32_t>(j);
-					cnt++;
+					const uint64_t j = j0 + u;
+					double r2 = 0.0;
+#pragma unroll
+					for (int a = 0; a < D; a++)
+					{
+						const double d = xi.v[a] - xj[u].v[a];
+						r2 += d * d; // -fmad=false: rounded product, then rounded sum, as uBLAS inner_prod
+					}
+					if ((j < je) && (j != i) && (r2 < nl2_lim)) // <=> sqrt(r2) < neighbor_length, bit for bit (EnvConst::nl2_lim)
+					{
+						if (FILL) nbr[base + cnt] = static_cast<uint32_t>(j);
+						cnt++;
+					}
 				}
 			}
 		}

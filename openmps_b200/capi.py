@@ -308,6 +308,12 @@ class GpuComputer:
         self._check(self.lib.mps_get_neighbors(self.h, _ptr(rowptr), _ptr(idx)))
         return rowptr, idx
 
+    def neighbor_counts(self):
+        """Neighbour-list lengths per particle (original order) without downloading the lists."""
+        rowptr = np.empty(self.count + 1, np.uint64)
+        self._check(self.lib.mps_get_neighbors(self.h, _ptr(rowptr), None))
+        return np.diff(rowptr).astype(np.int64)
+
     def csr(self):
         nnz = C.c_uint64()
         self._check(self.lib.mps_get_csr_nnz(self.h, C.byref(nnz)))

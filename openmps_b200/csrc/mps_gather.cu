@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 	// where this row's entries go
 	uint32_t* col = nullptr; double* val = nullptr; uint16_t* lcol = nullptr;
 	uint64_t w = 0;
-	uint32_t rstart[kMaxRanges], rlen[kMaxRanges], roff[kMaxRanges];
+	constexpr int NR = (D == 3) ? kMaxRanges : 3; // window ranges of a chunk: one per x[,y] column offset of the stencil (mps_chunk.cu)
+	uint32_t rstart[NR], rlen[NR], roff[NR];
 	if (CHUNKED)
 	{
 		const ChunkDesc* d = out.desc + out.chunk_of_row[i];
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 		const uint16_t* rowoff = lcol + nnz_pad;
 		w = rowoff[static_cast<uint32_t>(i) - d->row_begin];
 #pragma unroll
-		for (int k = 0; k < kMaxRanges; k++) { rstart[k] = d->range_start[k]; rlen[k] = d->range_len[k]; roff[k] = d->range_off[k]; }
+		for (int k = 0; k < NR; k++) { rstart[k] = d->range_start[k]; rlen[k] = d->range_len[k]; roff[k] = d->range_off[k]; }
 	}
 	else
 	{
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) k_ppe_fill(uint64_t first, uint64_t 
 		{
 			uint32_t l = 0xffffu;
 #pragma unroll
-			for (int k = kMaxRanges - 1; k >= 0; k--) { const uint32_t o = j - rstart[k]; if (o < rlen[k]) l = roff[k] + o; }
+			for (int k = NR - 1; k >= 0; k--) { const uint32_t o = j - rstart[k]; if (o < rlen[k]) l = roff[k] + o; }
 			lcol[w] = static_cast<uint16_t>(l);
 		}
 		else col[w] = j;

@@ -315,6 +315,51 @@ def test_preconditioned_solve_same_answer_far_fewer_sweeps(make, steps, monkeypa
     assert it_pcg * 5 <= it_plain, (it_pcg, it_plain)
 
 
+@pytest.mark.parametrize("make,count,lattice_nbrs", [
+    (lambda: scenes.central_gravity(half=1000, l0=5e-5), 4004001, 24),     # BASELINE.json configs[2] (C3): 2001^2 particles, 2-D
+    (lambda: scenes.dambreak3d(1.36e-3), 12244936, None),                  # BASELINE.json configs[3] (C4): 12.2M particles, 3-D
+])
+def test_full_size_properties_c3_c4(make, count, lattice_nbrs, monkeypatch):
+    """BASELINE.json configs 3 and 4 at FULL size: too big for an oracle diff (the CPU code needs minutes per step), so
+    size-independent properties, all evaluated on the device or on O(n) downloads:
+    the first step's system solved twice from the same state — by the reference's plain CG (MPS_CG_PRECOND=0) and by the
+    preconditioned CG — gives the same pressures to the CG tolerance, both recurrence residuals are inside the stopping rule,
+    the preconditioned solve makes >= 5x fewer sweeps; neighbour counts are symmetric in total (sum of counts is even), no
+    particle lists itself more often than the cell stencil allows, lattice-interior particles have the lattice count and n = n0."""
+    sc = make()
+    assert sc.count == count
+    out = {}
+    for precond in ("0", "1"):
+        monkeypatch.setenv("MPS_CG_PRECOND", precond)
+        g = capi.GpuComputer.from_scene(sc)
+        g.set_dt(sc.env.max_dt, True)
+        g.stage("search"); g.stage("density")
+        if precond == "1":
+            cnt = g.neighbor_counts()
+            assert int(cnt.sum()) % 2 == 0                                       # j in N(i) <=> i in N(j)
+            assert cnt.max() <= (3 ** sc.env.dim) * g.grid_capacity()
+            n_now = g.state()["n"]
+            n0 = g.env_values()["n0"]
+            if lattice_nbrs is not None:
+                # central gravity: every particle sits on the lattice at rest; the centre particle is far from the free surface
+                centre = int(np.argmin((sc.x ** 2).sum(axis=1)))
+                assert cnt[centre] == lattice_nbrs and abs(n_now[centre] - n0) <= 1e-9 * n0
+            assert np.isfinite(n_now).all() and (n_now[sc.type == 0] >= n0 * (1 - 1e-12)).all()   # N = max(n, n0), Computer.hpp:826
+        for st in ("ecs", "explicit", "density", "savex", "setppe", "solveppe"):
+            g.stage(st)
+        x = g.vec("x")
+        stt = g.stats()
+        assert np.isfinite(x).all()
+        assert stt.last_rr <= sc.env.eps ** 2 * stt.last_rr0, (precond, stt.last_rr, stt.last_rr0)
+        out[precond] = (x, g.last_iterations(), stt.mg_levels)
+        g.close()
+    (x_plain, it_plain, lv_plain), (x_pcg, it_pcg, lv_pcg) = out["0"], out["1"]
+    print(f"{count} particles: plain CG {it_plain} iterations, preconditioned {it_pcg} on {lv_pcg} levels")
+    assert lv_plain == 0 and lv_pcg >= 4
+    assert rel_err(x_pcg, x_plain) <= CG_TOL
+    assert it_pcg * 5 <= it_plain, (it_pcg, it_plain)
+
+
 def _wall_motion_positions(base, t, amp, vel, omega, phase, t0, t1):
     tau = min(max(t - t0, 0.0), t1 - t0)
     return base + np.asarray(vel) * tau + np.asarray(amp) * (np.sin(omega * tau + phase) - np.sin(phase))

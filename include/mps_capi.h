@@ -123,7 +123,8 @@ int mps_set_wall_motion(mps_handle h, uint64_t n, const uint64_t* ids, const mps
 int mps_determine_dt(mps_handle h, double* dt);           /* replaces Computer::DetermineDt, Computer.hpp:759-777 */
 int mps_forward_time(mps_handle h, double dt);            /* replaces Computer::ForwardTime(dt), Computer.hpp:1700-1742 */
 int mps_forward_time_auto(mps_handle h);                  /* replaces Computer::ForwardTime(),   Computer.hpp:1745-1751 */
-/* the driver's inner loop `while (T() < nextOutputT) ForwardTime()` (Main.cpp:370-376) without per-step host round trips */
+/* the driver's inner loop `while (T() < nextOutputT) ForwardTime()` (Main.cpp:370-376) as one call: dt, t and the loop condition
+ * are evaluated from device-resident scalars; each step still reads back two words (neighbour-list size, status) */
 int mps_run_until(mps_handle h, double t_next, uint64_t* steps);
 /* `steps` x ForwardTime() timed with CUDA events on the handle's stream (device time, milliseconds) */
 int mps_run_steps(mps_handle h, uint64_t steps, double* device_ms);
@@ -200,8 +201,8 @@ int mps_observe(mps_handle h, const mps_observe_params* params, mps_observables*
  * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,
  * a file ...), every rank attaches it to its handle BEFORE the first step and then adds the SAME particles in the same
  * order.  The particle state is replicated; each rank computes the x-slab [own_first, own_last) of the cell-sorted slots
- * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu.  NCCL carries the per-stage field
- * all-gathers; the CG iteration itself runs over peer memory (mps_comm_mode). */
+ * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu.  NCCL carries the set-up only (the
+ * unique id, the CUDA IPC handles); halo gathers, the solve's halo and its dot products run over peer memory (mps_comm_mode). */
 int mps_comm_unique_id(void* out128);
 int mps_comm_init(mps_handle h, int rank, int nranks, const void* id128);
 int mps_comm_info(mps_handle h, int* rank, int* nranks, uint64_t* own_first, uint64_t* own_last);

@@ -1,16 +1,20 @@
-// mps_comm.cu — multi-GPU: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+// mps_comm.cu — multi-GPU: one process per GPU, coupled over NVLink 5 / NVSwitch peer memory (NCCL for set-up and as a fallback).
 //
 // Decomposition (DESIGN.md "multi-GPU"): the cell-sorted slot order is x-major, so a contiguous range of slots IS an
-// x-slab of the domain, and equal slot counts give equal particle counts per rank whatever the shape of the fluid (the
-// dam break starts in the left quarter of the tank; equal-width slabs would idle most GPUs — SURVEY H9).  Every rank
-// keeps the whole particle state (a few hundred bytes per particle) but COMPUTES only its slab: neighbour lists,
-// gather stages, PPE rows and the CG rows of its slots; what grows with the problem — neighbour list and matrix — is
-// therefore partitioned.  Exchanges, all on the solver's stream:
-//   * after the stages that move particles or set pressures: in-place ncclAllGather of the fields neighbours read
-//     (x, u after the explicit move, the pressure gradient and the stabiliser; P after the solve).  Re-sorting the
-//     replicated state every step replaces particle migration.
-//   * per CG iteration: the {r, p} values of the slab's rim that the neighbour's windows reach (ncclSend/ncclRecv with
-//     the two adjacent ranks, contiguous slot ranges, no packing) and two ncclAllReduce of one double (p.Ap, r.r).
+// x-slab of the domain.  Every step the slabs are re-cut between cell columns so that every rank gets an equal share of a
+// per-type work model (k_slab_bounds, mps_grid.cu) whatever the shape of the fluid (the dam break starts in the left
+// quarter of the tank; equal-width slabs would idle most GPUs — SURVEY H9).  Every rank keeps the whole particle state (a few
+// hundred bytes per particle) but COMPUTES only its slab: neighbour lists, gather stages, PPE rows and the CG rows of its
+// slots; what grows with the problem — neighbour list and matrix — is therefore partitioned.  Exchanges, all on the
+// solver's stream, none through the host:
+//   * peer memory (mps_comm_mode 1): every rank exports one arena (mailboxes, barrier flags, the solve's {z, p} buffers, the
+//     level vectors of the preconditioner) and its state arrays through CUDA IPC.  After the stages that move particles or set
+//     pressures every rank PULLS the halo (one cell column of each adjacent rank: a contiguous slot range) straight from the
+//     owners between two flag barriers (k_peer_barrier, k_peer_gather); one full gather of x, u, p, n ends the step.
+//     Re-sorting the replicated state every step replaces particle migration.  The solve is ONE persistent kernel per rank
+//     (mps_cg.cu): halo of {z, p} pulled once per iteration, dot products through flag-in-data mailboxes.
+//   * NCCL (mode 2: the ranks cannot map each other's memory, or MPS_COMM_NCCL_ONLY=1): in-place ncclAllGather of the
+//     fields, a stepwise plain CG with ncclSend/ncclRecv of the rim and ncclAllReduce of the dot products.
 // The reference has nothing to compare with here (single process, OpenMP); parity is 1 GPU vs N GPUs on the same input.
 //
 // NCCL is loaded with dlopen so that the library neither links against a particular libnccl nor fights the copy that

@@ -241,7 +241,11 @@ int mps_get_cg_profile_stages(mps_handle h, uint64_t* out /* 64 */);
  *                          the top level and its size limit (64 cells) of the preconditioner's V-cycle
  *   MPS_CG_ADAPTIVE=0      freeze the CG kernel's CTA split (uniform): runs become bit-identical; default: re-balanced every solve
  *   MPS_COMM_NCCL_ONLY=1   several GPUs: couple the ranks through NCCL between per-phase launches instead of peer memory
- *   MPS_CG_WARPS, MPS_CG_LPR, MPS_CG_STAGES, MPS_CG_COST_FIXED   chunk geometry / pipeline depth / load-balance model of k_cg_stream
+ *   MPS_CG_WARPS, MPS_CG_LPR, MPS_CG_STAGES, MPS_CG_PRODUCERS, MPS_CG_COST_FIXED   consumer warps / lanes per row / ring depth /
+ *                          producer warps (1..4) / load-balance model of the streaming CG kernels
+ *   MPS_MG_DIST_CELLS      several GPUs: level 0 of the cell hierarchy is distributed when it has more cells than this (150000)
+ *   MPS_SLAB_WEIGHTS=f,w,d several GPUs: work per Fluid / Wall / Dummy particle in the slab split (8,4,1)
+ *   MPS_ALLOC_SLACK=0      no head-room on growing buffers and exact blob sizing (blocks that only just fit one GPU; default 25 %)
  *   MPS_CG_GENERIC=1       solve assembled systems with the generic CSR kernel (k_cg_solve) instead of the streaming one
  */
 

@@ -1038,7 +1038,6 @@ __device__ __forceinline__ double stencil_dot_prolong(const uint32_t* __restrict
 	return acc;
 }
 
-constexpr uint32_t kMgSmallCells = 256;  // levels with at most this many cells are run by CTA 0 alone between block barriers
 
 // several ranks: which compact cells of level l lie left of cell column `col` (asked for level 0 only: any column is a cell boundary there)
 __device__ __forceinline__ uint32_t level_cell_begin(const MgLevelPtrs& lv, const int l, const uint32_t col)
@@ -1338,7 +1337,7 @@ __global__ void __launch_bounds__((D == 3 ? kMaxStreamWarps : kStreamWarps2d) * 
 	while (L < m.levels && *m.lv[L - 1].count > m.top_cells) L++;
 	if (MG && L < dc.k + 1) L = dc.k + 1;
 	int Ls = 0; // first level small enough for CTA 0 alone
-	while (Ls < L && *m.lv[Ls].count > kMgSmallCells) Ls++;
+	while (Ls < L && *m.lv[Ls].count > m.small_cells) Ls++;
 	if (MG && Ls < dc.k + 1) Ls = dc.k + 1; // distributed and gathered levels are always run by the whole grid
 	// this warp's rows in phase 2: a cell-aligned range, this rank's level-0 cells split evenly over all warps of the grid
 	uint64_t rb, re;
@@ -1660,7 +1659,7 @@ cudaError_t launch_pcg(mps_solver* s)
 	}
 	L.a.r = c.r.p;
 	MgArgs m{};
-	m.levels = g.levels; m.top_sweeps = g.top_sweeps; m.top_cells = g.top_cells; m.gamma = g.gamma;
+	m.levels = g.levels; m.top_sweeps = g.top_sweeps; m.top_cells = g.top_cells; m.small_cells = g.small_cells; m.gamma = g.gamma;
 	m.crow = g.crow.p; m.cstart = g.cstart.p; m.dinv0 = g.dinv0.p; m.r = c.r.p;
 	double* arena_vec = MG ? comm_mg_section(s, s->comm.rank) : nullptr;
 	if (MG && (!arena_vec || !g.in_arena)) return cudaErrorInvalidValue;

@@ -188,6 +188,7 @@ struct MgArgs
 	int levels;              // levels built (the kernel stops at the first one with <= top_cells cells)
 	int top_sweeps;          // extra damped-Jacobi sweeps on the top level
 	uint32_t top_cells;
+	uint32_t small_cells;    // levels with at most this many cells are run by CTA 0 alone between block barriers
 	double gamma;            // over-correction of every coarse-grid correction
 	const uint32_t* crow;    // [rows] level-0 cell of a row (kMgNone for Disabled rows)
 	const uint64_t* cstart;  // [cells0 + 1] first row of every level-0 cell; last entry = rows that lie in cells

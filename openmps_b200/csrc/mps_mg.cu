@@ -314,6 +314,7 @@ void mg_configure(mps_solver* s)
 	if (const char* v = std::getenv("MPS_MG_GAMMA")) mg.gamma = std::atof(v);
 	if (const char* v = std::getenv("MPS_MG_TOP_SWEEPS")) { const int k = std::atoi(v); if (k >= 0 && k <= 64) mg.top_sweeps = k; }
 	if (const char* v = std::getenv("MPS_MG_TOP_CELLS")) { const int k = std::atoi(v); if (k >= 1) mg.top_cells = static_cast<uint32_t>(k); }
+	if (const char* v = std::getenv("MPS_MG_SMALL_CELLS")) { const int k = std::atoi(v); if (k >= 0) mg.small_cells = static_cast<uint32_t>(k); }
 	if (const char* v = std::getenv("MPS_MG_DIST_CELLS")) { const long long k = std::atoll(v); if (k >= 0) mg.dist_cells = static_cast<uint64_t>(k); }
 	long long d[3] = { 1, 1, 1 };
 	for (int a = 0; a < D; a++) d[a] = s->env.grid_n[a];

@@ -114,6 +114,7 @@ struct MgBuffers
 	double omega = 0.8, gamma = 1.8;
 	int top_sweeps = 4;
 	uint32_t top_cells = 64;
+	uint32_t small_cells = 256;      // MPS_MG_SMALL_CELLS
 	uint64_t cells0 = 0;             // occupied cells of the neighbour grid at the last sort (read back with the list size)
 	MgLevelBufs lv[kMgMaxLevels];
 	DevBuf<uint32_t> crow;

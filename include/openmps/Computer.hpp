@@ -161,6 +161,7 @@ namespace { namespace OpenMps
 		// host mirror of the particles in insertion order (reference :463); refreshed from the device when stale
 		mutable std::vector<Particle> particles;
 		mutable bool particlesStale = false;
+		std::size_t lastRunSteps = 0;
 
 		Environment environment;
 		Grid grid;
@@ -480,9 +481,12 @@ namespace { namespace OpenMps
 			double t = 0, dt = 0;
 			if (mps_get_time(device.h, &t, &dt) == MPS_OK) { environment.Dt() = dt; environment.SetT(t); }
 			typesStale = true; // particles may have left the grid during the interval
+			lastRunSteps = static_cast<std::size_t>(steps);
 			Check(rc);
 			return static_cast<std::size_t>(steps);
 		}
+		// steps the last RunUntil() completed — also when it ended in an exception (the failed step is not counted)
+		std::size_t LastRunSteps() const { return lastRunSteps; }
 
 		// Wall motion without the host in the loop: the listed non-fluid particles (empty list: all of them) follow
 		//   positionWall(i, t, dt) + velocity * tau + amplitude * (sin(omega * tau + phase) - sin(phase)),  tau = clamp(t - t_begin, 0, t_end - t_begin)

@@ -544,8 +544,8 @@ int mps_run_until(mps_handle s, double t_next, uint64_t* steps)
 	while (s->h_sc->t < t_next) // Main.cpp:370
 	{
 		rc = mps_forward_time_auto(s);
+		if (rc) break; // the failed step is not counted: *steps = steps completed, as the driver's error line reports them
 		k++;
-		if (rc) break;
 	}
 	if (steps) *steps = k;
 	return rc;

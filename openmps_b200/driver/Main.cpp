@@ -190,6 +190,7 @@ int main(const int argc, const char* const argv[])
 			catch (const decltype(computer)::Exception& ex)
 			{
 				writer.Finish(); // pending progress lines first
+				iteration += computer.LastRunSteps(); // the steps of this interval that completed before the failing one
 				tComputer = computer.GetEnvironment().T();
 				std::cout << "!!!!ERROR!!!!" << std::endl
 					<< "#" << (outputCount + outputIterationOffset) << ": t=" << tComputer << " (" << iteration << ")" << std::endl

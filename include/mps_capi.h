@@ -201,8 +201,9 @@ int mps_observe(mps_handle h, const mps_observe_params* params, mps_observables*
  * One process per GPU.  Rank 0 obtains an NCCL unique id (128 bytes), the launcher distributes it (torch.distributed, MPI,
  * a file ...), every rank attaches it to its handle BEFORE the first step and then adds the SAME particles in the same
  * order.  The particle state is replicated; each rank computes the x-slab [own_first, own_last) of the cell-sorted slots
- * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu.  NCCL carries the set-up only (the
- * unique id, the CUDA IPC handles); halo gathers, the solve's halo and its dot products run over peer memory (mps_comm_mode). */
+ * (neighbour lists, gather stages, PPE rows, CG rows); see openmps_b200/csrc/mps_comm.cu.  NCCL carries the set-up (the unique id, the
+ * CUDA IPC handles) and two small collectives per step (coarse operator sum, halo extents); halo gathers, the solve's halo and its
+ * dot products run over peer memory (mps_comm_mode). */
 int mps_comm_unique_id(void* out128);
 int mps_comm_init(mps_handle h, int rank, int nranks, const void* id128);
 int mps_comm_info(mps_handle h, int* rank, int* nranks, uint64_t* own_first, uint64_t* own_last);

@@ -6,7 +6,7 @@
 // quarter of the tank; equal-width slabs would idle most GPUs — SURVEY H9).  Every rank keeps the whole particle state (a few
 // hundred bytes per particle) but COMPUTES only its slab: neighbour lists, gather stages, PPE rows and the CG rows of its
 // slots; what grows with the problem — neighbour list and matrix — is therefore partitioned.  Exchanges, all on the
-// solver's stream, none through the host:
+// solver's stream (NCCL itself only for set-up, the per-step sum of the first replicated coarse operator and the halo extents):
 //   * peer memory (mps_comm_mode 1): every rank exports one arena (mailboxes, barrier flags, the solve's {z, p} buffers, the
 //     level vectors of the preconditioner) and its state arrays through CUDA IPC.  After the stages that move particles or set
 //     pressures every rank PULLS the halo (one cell column of each adjacent rank: a contiguous slot range) straight from the

@@ -61,6 +61,7 @@ def _port_and_gpu(sc):
 @pytest.mark.parametrize("make,steps,xtol", [
     (lambda: scenes.dambreak2d(), 60, 1e-8),
     (lambda: scenes.static_pressure(width=16, height=24), 30, 1e-8),
+    (lambda: scenes.static_pressure(), 30, 1e-8),                      # BASELINE.json configs[0] at its default resolution: 6 040 particles
     (lambda: scenes.central_gravity(half=14), 30, 1e-8),
     (lambda: scenes.dambreak3d(l0=0.035), 6, 1e-8),
     (lambda: scenes.lattice(3, 6, 0.1, 2.1, jitter=0.05, max_dt=1e-3), 5, 1e-8),
@@ -102,6 +103,34 @@ def test_seeded_jitter_neighbour_lists_bit_exact_2d_and_3d():
         p.set_state(u=u); g.set_state(u=u)
         for i in rng.integers(0, sc.count, 8):
             assert abs(p.dndt(int(i)) - g.dndt(int(i))) <= 1e-12 * max(1.0, abs(p.dndt(int(i))))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_search_threshold_is_exact_at_the_boundary(dim):
+    """k_search tests r2 < T with T the smallest double whose correctly rounded root is >= NL instead of sqrt(r2) < NL
+    (EnvConst::nl2_lim).  Adversarial input: pairs at distances NL * (1 + t) for t from a few ulp to +-3e-3 around the threshold,
+    far from the origin, in random directions.  The lists must equal the CPU restatement's (which evaluates the reference's
+    R(x_i, x_j) < neighborLength, Computer.hpp:743) entry for entry."""
+    rng = np.random.default_rng(77 + dim)
+    l0, q = 1e-3, 2.4
+    nl = q * l0 * 1.2
+    span = np.array([4000 * l0] + [40 * l0] * (dim - 1))   # long in x only, so that the grid stays small
+    m = 6000
+    anchors = rng.uniform(0.25 * span, 0.9 * span, (m, dim))
+    t = np.concatenate([np.linspace(-3e-3, 3e-3, m // 2), rng.choice([-1, 1], m // 4) * 2.0 ** -rng.integers(30, 52, m // 4),
+                        rng.normal(0, 3e-4, m - m // 2 - m // 4)])
+    d = rng.normal(size=(m, dim)); d /= np.linalg.norm(d, axis=1)[:, None]
+    partners = anchors + d * (nl * (1.0 + t))[:, None]
+    x = np.ascontiguousarray(np.concatenate([anchors, partners]))
+    typ = np.zeros(len(x), np.int32); typ[::7] = scenes.WALL
+    env = scenes.Env(dim, 1e-3, 0.1, 9.8, 998.2, 1.004e-6, q, l0, tuple([0.0] * dim), tuple(float(v) for v in span), 1e-10)
+    sc = scenes.Scene(env, x, np.zeros_like(x), np.zeros(len(x)), np.zeros(len(x)), typ, "threshold")
+    p, g = _port_and_gpu(sc)
+    p.set_dt(1e-3, True); g.set_dt(1e-3, True)
+    p.stage("search"); g.stage("search")
+    a, b = p.neighbors(), g.neighbors()
+    assert int(a[0][-1]) > m // 3                       # about half of the engineered pairs are inside
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_first_disable_event_matches():

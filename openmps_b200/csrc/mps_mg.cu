@@ -74,58 +74,91 @@ __global__ void __launch_bounds__(kThreads) k_mg_occ_up(uint64_t dense_hi, Dims 
 	flag_hi[C] = any;
 }
 
-// dense -> compact: key[rank] = dense index of the occupied cell
-__global__ void __launch_bounds__(kThreads) k_mg_compact(uint64_t dense, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ rank, uint32_t* __restrict__ key)
+// ---- compact ids, neighbour / parent tables and child tables of ALL levels in one launch each (the upper levels are a few hundred
+//      cells: a launch per level and table was ~25 launches of a few microseconds per step).  Block b works on level l with
+//      bb[l] <= b < bb[l + 1].
+//      compact:  dense -> compact, key[rank] = dense index of the occupied cell
+//      topology: per occupied cell its 3^D neighbours (compact ids) and its parent block at the next level
+//      children: per occupied block of level l + 1 its 2^D children at level l ----
+struct MgLevelDev
 {
-	const uint64_t c = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-	if (c < dense && flag[c]) key[rank[c]] = static_cast<uint32_t>(c);
+	uint64_t dense, bound;
+	Dims dims;
+	const uint32_t* flag; const uint64_t* rank;
+	uint32_t* key; uint32_t* nbr; uint32_t* parent; uint32_t* child;
+};
+struct MgBatch
+{
+	int levels;
+	MgLevelDev lv[kMgMaxLevels];
+};
+struct MgBlocks { uint32_t bb[kMgMaxLevels + 1]; };
+
+__device__ __forceinline__ int level_of_block(const MgBlocks& b, const int levels, uint32_t& local)
+{
+	int l = 0;
+	while (l + 1 < levels && blockIdx.x >= b.bb[l + 1]) l++;
+	local = blockIdx.x - b.bb[l];
+	return l;
 }
 
-// per occupied cell: its 3^D neighbours (compact ids) and its parent block at the next level (hi arrays may be null at the last level)
+__global__ void __launch_bounds__(kThreads) k_mg_compact_all(MgBatch m, MgBlocks b)
+{
+	uint32_t lb; const int l = level_of_block(b, m.levels, lb);
+	const MgLevelDev& v = m.lv[l];
+	const uint64_t c = static_cast<uint64_t>(lb) * kThreads + threadIdx.x;
+	if (c < v.dense && v.flag[c]) v.key[v.rank[c]] = static_cast<uint32_t>(c);
+}
+
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_mg_topology(uint64_t bound, const uint64_t* __restrict__ count, Dims lo, Dims hi,
-	const uint32_t* __restrict__ key, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ rank, const uint64_t* __restrict__ rank_hi,
-	uint32_t* __restrict__ nbr, uint32_t* __restrict__ parent)
+__global__ void __launch_bounds__(kThreads) k_mg_topology_all(MgBatch m, MgBlocks b)
 {
 	constexpr int K = (D == 3) ? 27 : 9;
-	const uint64_t cc = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-	if (cc >= bound || cc >= *count) return;
-	long long c[3]; decode<D>(key[cc], lo, c);
+	uint32_t lb; const int l = level_of_block(b, m.levels, lb);
+	const MgLevelDev& v = m.lv[l];
+	const bool last = (l + 1 == m.levels);
+	const uint64_t cc = static_cast<uint64_t>(lb) * kThreads + threadIdx.x;
+	if (cc >= v.bound || cc >= v.rank[v.dense]) return; // rank[dense] = occupied cells of the level
+	const Dims lo = v.dims;
+	long long c[3]; decode<D>(v.key[cc], lo, c);
 	int s = 0;
 	for (int ox = -1; ox <= 1; ox++)
 		for (int oy = (D == 3 ? -1 : 0); oy <= (D == 3 ? 1 : 0); oy++)
 			for (int oz = -1; oz <= 1; oz++, s++)
 			{
-				long long b[3];
-				b[0] = c[0] + ox;
-				if (D == 3) b[1] = c[1] + oy;
-				b[D - 1] = c[D - 1] + oz;
+				long long q[3];
+				q[0] = c[0] + ox;
+				if (D == 3) q[1] = c[1] + oy;
+				q[D - 1] = c[D - 1] + oz;
 				uint32_t id = kMgNone;
-				if (inside<D>(b, lo))
+				if (inside<D>(q, lo))
 				{
-					const uint64_t k = encode<D>(b, lo);
-					if (flag[k]) id = static_cast<uint32_t>(rank[k]);
+					const uint64_t k = encode<D>(q, lo);
+					if (v.flag[k]) id = static_cast<uint32_t>(v.rank[k]);
 				}
-				nbr[cc * K + s] = id;
+				v.nbr[cc * K + s] = id;
 			}
-	if (parent)
+	if (!last)
 	{
+		const MgLevelDev& h = m.lv[l + 1];
 		long long p[3];
 #pragma unroll
 		for (int a = 0; a < D; a++) p[a] = c[a] >> 1;
-		parent[cc] = static_cast<uint32_t>(rank_hi[encode<D>(p, hi)]);
+		v.parent[cc] = static_cast<uint32_t>(h.rank[encode<D>(p, h.dims)]);
 	}
 }
 
-// per occupied block of level l + 1: its children at level l
+// blocks of level l >= 1 (bb counts levels 1 .. levels - 1 as 0 .. levels - 2)
 template<int D>
-__global__ void __launch_bounds__(kThreads) k_mg_children(uint64_t bound, const uint64_t* __restrict__ count_hi, Dims lo, Dims hi,
-	const uint32_t* __restrict__ key_hi, const uint32_t* __restrict__ flag_lo, const uint64_t* __restrict__ rank_lo, uint32_t* __restrict__ child)
+__global__ void __launch_bounds__(kThreads) k_mg_children_all(MgBatch m, MgBlocks b)
 {
 	constexpr int CH = 1 << D;
-	const uint64_t C = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-	if (C >= bound || C >= *count_hi) return;
-	long long cc[3]; decode<D>(key_hi[C], hi, cc);
+	uint32_t lb; const int l = level_of_block(b, m.levels - 1, lb) + 1;
+	const MgLevelDev& hi = m.lv[l];
+	const MgLevelDev& lo = m.lv[l - 1];
+	const uint64_t C = static_cast<uint64_t>(lb) * kThreads + threadIdx.x;
+	if (C >= hi.bound || C >= hi.rank[hi.dense]) return;
+	long long cc[3]; decode<D>(hi.key[C], hi.dims, cc);
 #pragma unroll
 	for (int q = 0; q < CH; q++)
 	{
@@ -133,12 +166,12 @@ __global__ void __launch_bounds__(kThreads) k_mg_children(uint64_t bound, const 
 #pragma unroll
 		for (int a = 0; a < D; a++) c[a] = 2 * cc[a] + ((q >> (D - 1 - a)) & 1);
 		uint32_t id = kMgNone;
-		if (inside<D>(c, lo))
+		if (inside<D>(c, lo.dims))
 		{
-			const uint64_t k = encode<D>(c, lo);
-			if (flag_lo[k]) id = static_cast<uint32_t>(rank_lo[k]);
+			const uint64_t k = encode<D>(c, lo.dims);
+			if (lo.flag[k]) id = static_cast<uint32_t>(lo.rank[k]);
 		}
-		child[C * CH + q] = id;
+		hi.child[C * CH + q] = id;
 	}
 }
 
@@ -246,27 +279,24 @@ cudaError_t setup(mps_solver* s)
 		L += 1;
 		MPS_TRY(launch_exclusive_scan_u32_to_u64(hi.flag.p, hi.rank.p, hi.dense, s->scan_tmp, st, &L));
 	}
-	for (int l = 0; l < mg.levels; l++)
 	{
-		MgLevelBufs& lv = mg.lv[l];
-		k_mg_compact<<<blocks_for(lv.dense, kThreads), kThreads, 0, st>>>(lv.dense, lv.flag.p, lv.rank.p, lv.key.p);
-		L += 1;
-	}
-	for (int l = 0; l < mg.levels; l++)
-	{
-		MgLevelBufs& lv = mg.lv[l];
-		const bool last = (l + 1 == mg.levels);
-		const MgLevelBufs& hi = mg.lv[last ? l : l + 1];
-		k_mg_topology<D><<<blocks_for(lv.bound, kThreads), kThreads, 0, st>>>(lv.bound, lv.rank.p + lv.dense, dims_of(lv), dims_of(hi), lv.key.p, lv.flag.p,
-			lv.rank.p, last ? nullptr : hi.rank.p, lv.nbr.p, last ? nullptr : lv.parent.p);
-		L += 1;
-		if (l > 0)
+		MgBatch m{};
+		m.levels = mg.levels;
+		MgBlocks bc{}, bt{}, bh{};
+		for (int l = 0; l < mg.levels; l++)
 		{
-			const MgLevelBufs& lo = mg.lv[l - 1];
-			k_mg_children<D><<<blocks_for(lv.bound, kThreads), kThreads, 0, st>>>(lv.bound, lv.rank.p + lv.dense, dims_of(lo), dims_of(lv), lv.key.p, lo.flag.p,
-				lo.rank.p, lv.child.p);
-			L += 1;
+			MgLevelBufs& lv = mg.lv[l];
+			MgLevelDev& d = m.lv[l];
+			d.dense = lv.dense; d.bound = lv.bound; d.dims = dims_of(lv);
+			d.flag = lv.flag.p; d.rank = lv.rank.p; d.key = lv.key.p; d.nbr = lv.nbr.p; d.parent = lv.parent.p; d.child = (l > 0) ? lv.child.p : nullptr;
+			bc.bb[l + 1] = bc.bb[l] + blocks_for(lv.dense, kThreads);
+			bt.bb[l + 1] = bt.bb[l] + blocks_for(lv.bound, kThreads);
+			if (l > 0) bh.bb[l] = bh.bb[l - 1] + blocks_for(lv.bound, kThreads);
 		}
+		k_mg_compact_all<<<bc.bb[mg.levels], kThreads, 0, st>>>(m, bc);
+		k_mg_topology_all<D><<<bt.bb[mg.levels], kThreads, 0, st>>>(m, bt);
+		L += 2;
+		if (mg.levels > 1) { k_mg_children_all<D><<<bh.bb[mg.levels - 1], kThreads, 0, st>>>(m, bh); L += 1; }
 	}
 	// ---- rows <-> level-0 cells ----
 	MgLevelBufs& l0 = mg.lv[0];
@@ -326,7 +356,9 @@ void mg_configure(mps_solver* s)
 		for (int a = 0; a < 3; a++) { lv.dims[a] = d[a]; lv.dense *= static_cast<uint64_t>(d[a]); }
 		bool one = true;
 		for (int a = 0; a < D; a++) one = one && (d[a] == 1);
-		if (one) { l++; break; }
+		// the V-cycle stops at the first level with <= top_cells occupied cells (k_pcg_stream); a level whose whole bounding grid is
+		// that small is certainly the last one it can use: nothing above it needs to be built
+		if (one || lv.dense <= mg.top_cells) { l++; break; }
 		for (int a = 0; a < D; a++) d[a] = (d[a] + 1) / 2;
 	}
 	mg.levels = l;

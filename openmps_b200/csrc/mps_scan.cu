@@ -1,9 +1,11 @@
 // mps_scan.cu — device-wide exclusive prefix sum (u32 counts -> u64 offsets, n + 1 outputs), hand-written.
 //
-// Used three times per step: particles-per-cell -> cell_start (the reference's per-cell bucket, Grid.hpp:76,276-331,
-// becomes a start/end table), neighbour counts -> neighbour row pointers (Computer.hpp:594-612 keeps a fixed-stride table
-// instead), PPE row lengths -> CSR row pointers (replaces the serial uBLAS insertion, Computer.hpp:1337-1349).
-// Three passes (tile sums, scan of tile sums, tile scans): 2 reads + 1 write of the input, HBM-bound and tiny next to CG.
+// Used per step for: particles-per-cell -> cell_start (the reference's per-cell bucket, Grid.hpp:76,276-331, becomes a
+// start/end table), neighbour counts -> neighbour row pointers (Computer.hpp:594-612 keeps a fixed-stride table instead), PPE
+// row lengths -> CSR row pointers (replaces the serial uBLAS insertion, Computer.hpp:1337-1349), the chunk tables (mps_chunk.cu)
+// and the occupied-cell ranks of every level of the preconditioner's hierarchy (mps_mg.cu).
+// Long inputs: three passes (tile sums, scan of tile sums, tile scans): 2 reads + 1 write of the input, HBM-bound and tiny next
+// to CG.  Short inputs (<= 32 768 items): one block, one launch (k_scan_small).
 #include "mps_solver.h"
 
 namespace mps {
